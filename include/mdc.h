@@ -1,0 +1,168 @@
+/*
+ * mdc.h - C ABI of libmdc.so, the B200 (sm_100a) CNN2 / SV-datapath / FWHT hot path.
+ *
+ * The reference (peteroh23/ModulationDetectionCNN) has no FFI or plugin seam: its
+ * only inference entry points are the Keras calls in cnn.py and CNN.ipynb and the
+ * `layers_top` module port list in cnn_test_latest1.sv.  Each entry point below
+ * names the reference interface it stands in for; INTEGRATION.md shows the
+ * ctypes stub a maintainer of the reference would add to cnn.py.
+ *
+ * Conventions
+ *   - plain C, no exceptions across the boundary; every function returns an int
+ *     status: 0 = MDC_OK, negative = error.  mdc_last_error() returns a
+ *     thread-local, NUL-terminated description of the last failure.
+ *   - pointers named *_dev are CUDA device pointers owned by the caller (e.g. a
+ *     torch tensor's data_ptr()); pointers named *_host are host pointers.  The
+ *     library never frees caller memory.
+ *   - every device entry point takes an explicit stream (cudaStream_t passed as
+ *     void*), only enqueues work on it and does not synchronise.
+ *   - a handle belongs to one device; it is thread-compatible (one handle per
+ *     thread, or external locking).
+ *   - there is no CPU fallback: without a CUDA device every compute call fails
+ *     with MDC_ERR_CUDA.
+ */
+#ifndef MDC_H_
+#define MDC_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MDC_API __attribute__((visibility("default")))
+
+typedef struct mdc_handle_s* mdc_handle_t;
+
+/* status codes */
+enum {
+  MDC_OK = 0,
+  MDC_ERR_INVALID = -1,     /* bad argument / wrong model kind or mode for this call */
+  MDC_ERR_CUDA = -2,        /* CUDA runtime/driver error (text in mdc_last_error) */
+  MDC_ERR_NOT_READY = -3,   /* weights not (completely) set */
+  MDC_ERR_UNSUPPORTED = -4  /* shape outside what the kernels implement */
+};
+
+/* model kinds */
+enum {
+  MDC_MODEL_TINY = 0, /* TinyCNN2(F,C): CNN.ipynb cell 6 / the *.wts.h5 model_config */
+  MDC_MODEL_VT = 1    /* VT-CNN2(C):   examples-master/.../RML2016.10a_VTCNN2_example.ipynb:231-243 */
+};
+
+/* arithmetic modes */
+enum {
+  MDC_MODE_FP32 = 0,   /* fp32 FMA on CUDA cores (parity mode, <=1e-5 of the fp64 oracle) */
+  MDC_MODE_BF16 = 1,   /* VT-CNN2 only: bf16 operands, fp32 accumulate, tcgen05 tensor cores */
+  MDC_MODE_TF32X3 = 2, /* VT-CNN2 only: reserved (3xTF32 split), not implemented yet */
+  MDC_MODE_Q612 = 3    /* TinyCNN2 only: bit-exact 18-bit Q6.12 SystemVerilog datapath */
+};
+
+/* tensor ids for mdc_set_weights_f32 (Keras layouts: conv (kh,kw,cin,cout), dense (in,out)) */
+enum {
+  MDC_T_CONV1_K = 0, MDC_T_CONV1_B = 1,
+  MDC_T_CONV2_K = 2, MDC_T_CONV2_B = 3,   /* VT only */
+  MDC_T_DENSE1_K = 4, MDC_T_DENSE1_B = 5,
+  MDC_T_DENSE2_K = 6, MDC_T_DENSE2_B = 7  /* VT only */
+};
+
+/* options for mdc_set_option */
+enum {
+  MDC_OPT_FLATTEN_ORDER = 0 /* VT only. 0 = channels_last (row = pos*80+ch, Keras 2 / TF,
+                               default), 1 = channels_first (row = ch*132+pos, Keras 1 / Theano) */
+};
+
+/* FWHT output orderings */
+enum { MDC_FWHT_NATURAL = 0, MDC_FWHT_SEQUENCY = 1 };
+
+/* ---- lifetime --------------------------------------------------------------------------
+ * Replaces: building the Keras `Sequential` (cnn.py:104-115, CNN.ipynb cell 6).
+ * filters: TinyCNN2 F (3 or 10 in the shipped checkpoints; 1..16 accepted); ignored for VT.
+ * classes: C (3 for every shipped checkpoint, 11 for VT-CNN2; 1..16 accepted).
+ * device:  CUDA ordinal.                                                                  */
+MDC_API int mdc_create(int model_kind, int filters, int classes, int mode, int device,
+                       mdc_handle_t* out);
+MDC_API int mdc_destroy(mdc_handle_t h);
+MDC_API int mdc_set_option(mdc_handle_t h, int option, int value);
+
+/* ---- weights ---------------------------------------------------------------------------
+ * Replaces: model.load_weights(filepath) (cnn.py:147, CNN.ipynb cell 8) - the Python side
+ * parses the .h5 (h5lite.py) and hands each tensor over in its Keras layout.
+ * count must equal the tensor's element count for (model, F, C).  Synchronous.            */
+MDC_API int mdc_set_weights_f32(mdc_handle_t h, int tensor_id, const float* host_ptr, size_t count);
+
+/* Replaces: the ROM modules of cnn_test_latest1.sv (rom_cov :685-707, dense_bias :260-262,
+ * rom_dense_{i,q}_class{1,2,3} :719-3132) == the *.Weights.txt tables.  Literal contents,
+ * 18-bit signed values in int32:  conv_tab[3F] = {w0,w1,bias} per filter;  dense_bias[C];
+ * dense_tabs[2C][129F] ordered class0-I, class0-Q, class1-I, ...   Synchronous.          */
+MDC_API int mdc_set_weights_q612(mdc_handle_t h, const int32_t* conv_tab_host,
+                                 const int32_t* dense_bias_host, const int32_t* dense_tabs_host);
+
+/* ---- float inference -------------------------------------------------------------------
+ * Replaces: model.predict(X, batch_size) (cnn.py:198,237; CNN.ipynb cells 12,17,18).
+ * x_dev      f32 [n,2,128], row 0 = I, row 1 = Q, C-contiguous.
+ * probs_dev  f32 [n,C]  softmax probabilities                     (may be NULL)
+ * dense_dev  f32 [n,C]  last Dense output before softmax: TinyCNN2 Dense+ReLU
+ *                       (`model2` of CNN.ipynb cell 17), VT-CNN2 logits     (may be NULL)
+ * cls_dev    i32 [n]    argmax class, first maximum wins like np.argmax (may be NULL)
+ * hist_dev   u64 [C]    class histogram, ACCUMULATED into (caller zeroes)  (may be NULL)
+ * The fused argmax/histogram replace the per-row Python loops of cnn.py:205-211,241-247. */
+MDC_API int mdc_predict_f32(mdc_handle_t h, const float* x_dev, int64_t n, float* probs_dev,
+                            float* dense_dev, int32_t* cls_dev, unsigned long long* hist_dev,
+                            void* stream);
+
+/* Same call with HOST buffers (what a numpy caller has): copies x in chunks on internal
+ * streams, overlapping H2D / kernels / D2H, and returns when the outputs are in host memory.
+ * Pinned buffers make the copies asynchronous; pageable buffers work but serialise.
+ * hist_host u64[C] is overwritten (not accumulated).                                      */
+MDC_API int mdc_predict_f32_host(mdc_handle_t h, const float* x_host, int64_t n, float* probs_host,
+                                 float* dense_host, int32_t* cls_host,
+                                 unsigned long long* hist_host);
+
+/* ---- integer (SystemVerilog-exact) inference ------------------------------------------
+ * Replaces: one reset-to-done run of `layers_top` (cnn_test_latest1.sv:144-209) per frame,
+ * fed by `test_input`/`test_table` (:71-142).
+ * x_dev    i32 [n,256]: entries 0..127 = I, 128..255 = Q, 18-bit signed, sign-extended
+ *                       (the address map of test_table, sv:88-89,102).
+ * out_dev  i32 [n,C]    `out_data`: ReLU'd 32-bit accumulators, Q.12        (may be NULL)
+ * pre_dev  i32 [n,C]    `pre_out_data`: accumulators before the final ReLU  (may be NULL)
+ * cls_dev / hist_dev as above (argmax over out_data).                                    */
+MDC_API int mdc_predict_q612(mdc_handle_t h, const int32_t* x_dev, int64_t n, int32_t* out_dev,
+                             int32_t* pre_dev, int32_t* cls_dev, unsigned long long* hist_dev,
+                             void* stream);
+MDC_API int mdc_predict_q612_host(mdc_handle_t h, const int32_t* x_host, int64_t n,
+                                  int32_t* out_host, int32_t* pre_host, int32_t* cls_host,
+                                  unsigned long long* hist_host);
+
+/* ---- Walsh-Hadamard transform ----------------------------------------------------------
+ * Replaces: the FWHT spectrogram stage named in README.md:5 (no code in the reference).
+ * Unnormalised WHT of each row: in/out i32 [n_spectra, 2^log2_npt], wrap mod 2^32.
+ * log2_npt in [5,13]; in_dev == out_dev (in place) is allowed.                          */
+MDC_API int mdc_fwht_i32(const int32_t* in_dev, int32_t* out_dev, int64_t n_spectra, int log2_npt,
+                         int ordering, void* stream);
+MDC_API int mdc_fwht_i32_host(const int32_t* in_host, int32_t* out_host, int64_t n_spectra,
+                              int log2_npt, int ordering, int device);
+
+/* ---- caller-side epilogue --------------------------------------------------------------
+ * Replaces: the confusion-matrix loops of cnn.py:200-211,239-247 / CNN.ipynb cell 12.
+ * conf_dev u64 [C,C] accumulated: conf[true[i]][pred[i]] += 1.                           */
+MDC_API int mdc_confusion_i32(const int32_t* true_dev, const int32_t* pred_dev, int64_t n,
+                              int classes, unsigned long long* conf_dev, void* stream);
+
+/* ---- introspection ---------------------------------------------------------------------*/
+MDC_API const char* mdc_last_error(void);
+MDC_API const char* mdc_version(void);
+/* number of kernel launches this handle has enqueued so far (bench.py's gpu_launches)     */
+MDC_API int64_t mdc_launch_count(mdc_handle_t h);
+/* name of the dominant kernel of the handle's predict path and the CUDA-event time of its
+ * launches: mdc_profile_enable(h,1) makes every predict call bracket that kernel with
+ * events on the caller's stream; mdc_profile_read returns the accumulated milliseconds and
+ * launch count (synchronises those events) and resets the accumulators.                   */
+MDC_API int mdc_profile_enable(mdc_handle_t h, int on);
+MDC_API int mdc_profile_read(mdc_handle_t h, double* ms_total, int64_t* launches,
+                             const char** kernel_name);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MDC_H_ */

@@ -1,0 +1,476 @@
+// C-ABI entry points of libmdc.so (see include/mdc.h) and the host-buffer pipeline.
+#include <string.h>
+
+#include "mdc_internal.cuh"
+
+namespace mdc {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int DeviceBuffer::reserve(size_t n) {
+  if (n <= bytes) return MDC_OK;
+  if (ptr) {
+    MDC_CUDA(cudaFree(ptr));
+    ptr = nullptr;
+    bytes = 0;
+  }
+  n = (n + 255) & ~(size_t)255;
+  MDC_CUDA(cudaMalloc(&ptr, n));
+  bytes = n;
+  return MDC_OK;
+}
+void DeviceBuffer::release() {
+  if (ptr) cudaFree(ptr);
+  ptr = nullptr;
+  bytes = 0;
+}
+
+void prof_begin(mdc_handle_s* h, cudaStream_t s) {
+  if (!h->prof.on) return;
+  cudaEvent_t a, b;
+  cudaEventCreate(&a);
+  cudaEventCreate(&b);
+  cudaEventRecord(a, s);
+  h->prof.pending.emplace_back(a, b);
+}
+void prof_end(mdc_handle_s* h, cudaStream_t s) {
+  if (!h->prof.on || h->prof.pending.empty()) return;
+  cudaEventRecord(h->prof.pending.back().second, s);
+}
+
+// ------------------------------------------------------------------ host pipeline
+// Three streams (H2D, compute, D2H) over a ring of device slots, so that the copy of chunk
+// i+1, the kernels of chunk i and the read-back of chunk i-1 overlap.
+struct HostPipe {
+  static constexpr int kSlots = 3;
+  cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr;
+  cudaEvent_t e_h2d[kSlots] = {}, e_comp[kSlots] = {}, e_d2h[kSlots] = {};
+  DeviceBuffer x[kSlots], o0[kSlots], o1[kSlots], o2[kSlots];
+  DeviceBuffer hist;
+  int init() {
+    if (s_h2d) return MDC_OK;
+    MDC_CUDA(cudaStreamCreateWithFlags(&s_h2d, cudaStreamNonBlocking));
+    MDC_CUDA(cudaStreamCreateWithFlags(&s_comp, cudaStreamNonBlocking));
+    MDC_CUDA(cudaStreamCreateWithFlags(&s_d2h, cudaStreamNonBlocking));
+    for (int i = 0; i < kSlots; ++i) {
+      MDC_CUDA(cudaEventCreateWithFlags(&e_h2d[i], cudaEventDisableTiming));
+      MDC_CUDA(cudaEventCreateWithFlags(&e_comp[i], cudaEventDisableTiming));
+      MDC_CUDA(cudaEventCreateWithFlags(&e_d2h[i], cudaEventDisableTiming));
+    }
+    return hist.reserve(kMaxClasses * kMaxClasses * sizeof(unsigned long long));
+  }
+  void destroy() {
+    if (!s_h2d) return;
+    cudaStreamSynchronize(s_h2d); cudaStreamSynchronize(s_comp); cudaStreamSynchronize(s_d2h);
+    for (int i = 0; i < kSlots; ++i) {
+      cudaEventDestroy(e_h2d[i]); cudaEventDestroy(e_comp[i]); cudaEventDestroy(e_d2h[i]);
+      x[i].release(); o0[i].release(); o1[i].release(); o2[i].release();
+    }
+    hist.release();
+    cudaStreamDestroy(s_h2d); cudaStreamDestroy(s_comp); cudaStreamDestroy(s_d2h);
+    s_h2d = nullptr;
+  }
+};
+
+void destroy_pipe(mdc_handle_s* h) {
+  if (h->pipe) {
+    h->pipe->destroy();
+    delete h->pipe;
+    h->pipe = nullptr;
+  }
+}
+
+static int ensure_packed(mdc_handle_s* h) {
+  if (h->packed) return MDC_OK;
+  const int need_tiny[] = {MDC_T_CONV1_K, MDC_T_CONV1_B, MDC_T_DENSE1_K, MDC_T_DENSE1_B};
+  if (h->model == MDC_MODEL_TINY) {
+    for (int t : need_tiny)
+      MDC_REQUIRE(h->have[t], MDC_ERR_NOT_READY, "weights tensor %d not set (call mdc_set_weights_f32)", t);
+    if (int e = pack_tiny(h)) return e;
+  } else {
+    for (int t = 0; t < 8; ++t)
+      MDC_REQUIRE(h->have[t], MDC_ERR_NOT_READY, "weights tensor %d not set (call mdc_set_weights_f32)", t);
+    if (h->mode == MDC_MODE_FP32) {
+      if (int e = pack_vt_f32(h)) return e;
+    } else {
+      if (int e = pack_vt_bf16(h)) return e;
+    }
+  }
+  h->packed = true;
+  return MDC_OK;
+}
+
+static size_t tensor_count(const mdc_handle_s* h, int id) {
+  if (h->model == MDC_MODEL_TINY) {
+    switch (id) {
+      case MDC_T_CONV1_K: return (size_t)2 * h->F;
+      case MDC_T_CONV1_B: return (size_t)h->F;
+      case MDC_T_DENSE1_K: return (size_t)2 * 129 * h->F * h->C;
+      case MDC_T_DENSE1_B: return (size_t)h->C;
+      default: return 0;
+    }
+  }
+  switch (id) {
+    case MDC_T_CONV1_K: return 3 * 256;
+    case MDC_T_CONV1_B: return 256;
+    case MDC_T_CONV2_K: return (size_t)2 * 3 * 256 * 80;
+    case MDC_T_CONV2_B: return 80;
+    case MDC_T_DENSE1_K: return (size_t)kVtFlat * kVtH;
+    case MDC_T_DENSE1_B: return kVtH;
+    case MDC_T_DENSE2_K: return (size_t)kVtH * h->C;
+    case MDC_T_DENSE2_B: return (size_t)h->C;
+    default: return 0;
+  }
+}
+
+static int predict_f32_dev(mdc_handle_s* h, const float* x, int64_t n, float* probs, float* dense,
+                           int32_t* cls, unsigned long long* hist, cudaStream_t stream) {
+  if (h->model == MDC_MODEL_TINY) return launch_tiny_f32(h, x, n, probs, dense, cls, hist, stream);
+  if (h->mode == MDC_MODE_FP32) return launch_vt_f32(h, x, n, probs, dense, cls, hist, stream);
+  return launch_vt_bf16(h, x, n, probs, dense, cls, hist, stream);
+}
+
+}  // namespace mdc
+
+using namespace mdc;
+
+// ---- host-buffer variants --------------------------------------------------------------
+template <class In, class O0, class O1, class Launch>
+static int run_host_pipeline(mdc_handle_s* h, const In* x, int64_t n, O0* o0, O1* o1, int32_t* cls,
+                             unsigned long long* hist, int64_t chunk, Launch launch) {
+  if (!h->pipe) h->pipe = new HostPipe();
+  HostPipe& P = *h->pipe;
+  if (int e = P.init()) return e;
+  const int C = h->C;
+  constexpr int S = HostPipe::kSlots;
+  if (hist) MDC_CUDA(cudaMemsetAsync(P.hist.ptr, 0, C * sizeof(unsigned long long), P.s_comp));
+  for (int k = 0; k < S; ++k) {
+    if (int e = P.x[k].reserve((size_t)chunk * kFrameElems * sizeof(In))) return e;
+    if (o0) if (int e = P.o0[k].reserve((size_t)chunk * C * sizeof(O0))) return e;
+    if (o1) if (int e = P.o1[k].reserve((size_t)chunk * C * sizeof(O1))) return e;
+    if (cls) if (int e = P.o2[k].reserve((size_t)chunk * sizeof(int32_t))) return e;
+  }
+  int64_t i = 0;
+  for (int64_t s = 0; s < n; s += chunk, ++i) {
+    const int k = (int)(i % S);
+    const int64_t m = (n - s) < chunk ? (n - s) : chunk;
+    if (i >= S) MDC_CUDA(cudaStreamWaitEvent(P.s_h2d, P.e_comp[k], 0));
+    MDC_CUDA(cudaMemcpyAsync(P.x[k].ptr, x + s * kFrameElems, (size_t)m * kFrameElems * sizeof(In),
+                             cudaMemcpyHostToDevice, P.s_h2d));
+    MDC_CUDA(cudaEventRecord(P.e_h2d[k], P.s_h2d));
+    MDC_CUDA(cudaStreamWaitEvent(P.s_comp, P.e_h2d[k], 0));
+    if (i >= S) MDC_CUDA(cudaStreamWaitEvent(P.s_comp, P.e_d2h[k], 0));
+    if (int e = launch((const In*)P.x[k].ptr, m, o0 ? (O0*)P.o0[k].ptr : nullptr,
+                       o1 ? (O1*)P.o1[k].ptr : nullptr, cls ? (int32_t*)P.o2[k].ptr : nullptr,
+                       hist ? (unsigned long long*)P.hist.ptr : nullptr, P.s_comp))
+      return e;
+    MDC_CUDA(cudaEventRecord(P.e_comp[k], P.s_comp));
+    MDC_CUDA(cudaStreamWaitEvent(P.s_d2h, P.e_comp[k], 0));
+    if (o0) MDC_CUDA(cudaMemcpyAsync(o0 + s * C, P.o0[k].ptr, (size_t)m * C * sizeof(O0), cudaMemcpyDeviceToHost, P.s_d2h));
+    if (o1) MDC_CUDA(cudaMemcpyAsync(o1 + s * C, P.o1[k].ptr, (size_t)m * C * sizeof(O1), cudaMemcpyDeviceToHost, P.s_d2h));
+    if (cls) MDC_CUDA(cudaMemcpyAsync(cls + s, P.o2[k].ptr, (size_t)m * sizeof(int32_t), cudaMemcpyDeviceToHost, P.s_d2h));
+    MDC_CUDA(cudaEventRecord(P.e_d2h[k], P.s_d2h));
+  }
+  if (hist) {
+    MDC_CUDA(cudaStreamSynchronize(P.s_comp));
+    MDC_CUDA(cudaMemcpyAsync(hist, P.hist.ptr, C * sizeof(unsigned long long), cudaMemcpyDeviceToHost, P.s_d2h));
+  }
+  MDC_CUDA(cudaStreamSynchronize(P.s_d2h));
+  MDC_CUDA(cudaStreamSynchronize(P.s_comp));
+  return MDC_OK;
+}
+
+
+// ---- confusion matrix ------------------------------------------------------------------
+__global__ void confusion_kernel(const int* __restrict__ t, const int* __restrict__ p, long long n, int C,
+                                 unsigned long long* __restrict__ conf) {
+  __shared__ unsigned int sm[kMaxClasses * kMaxClasses];
+  for (int i = threadIdx.x; i < C * C; i += blockDim.x) sm[i] = 0;
+  __syncthreads();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int a = t[i], b = p[i];
+    if (a >= 0 && a < C && b >= 0 && b < C) atomicAdd(&sm[a * C + b], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C * C; i += blockDim.x)
+    if (sm[i]) atomicAdd(conf + i, (unsigned long long)sm[i]);
+}
+
+
+
+#define MDC_CHECK_HANDLE(h)                                                   \
+  MDC_REQUIRE((h) != nullptr, MDC_ERR_INVALID, "null handle");                \
+  MDC_CUDA(cudaSetDevice((h)->device))
+
+extern "C" {
+
+const char* mdc_last_error(void) { return g_err; }
+const char* mdc_version(void) { return "libmdc 0.1.0 (sm_100a)"; }
+
+int mdc_create(int model_kind, int filters, int classes, int mode, int device, mdc_handle_t* out) {
+  MDC_REQUIRE(out != nullptr, MDC_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  MDC_REQUIRE(model_kind == MDC_MODEL_TINY || model_kind == MDC_MODEL_VT, MDC_ERR_INVALID,
+              "unknown model kind %d", model_kind);
+  MDC_REQUIRE(classes >= 1 && classes <= kMaxClasses, MDC_ERR_UNSUPPORTED, "classes=%d outside 1..%d",
+              classes, kMaxClasses);
+  if (model_kind == MDC_MODEL_TINY) {
+    MDC_REQUIRE(filters >= 1 && filters <= kMaxFilters, MDC_ERR_UNSUPPORTED, "filters=%d outside 1..%d",
+                filters, kMaxFilters);
+    MDC_REQUIRE(mode == MDC_MODE_FP32 || mode == MDC_MODE_Q612, MDC_ERR_INVALID,
+                "TinyCNN2 supports MDC_MODE_FP32 and MDC_MODE_Q612, not mode %d", mode);
+  } else {
+    MDC_REQUIRE(mode == MDC_MODE_FP32 || mode == MDC_MODE_BF16, MDC_ERR_UNSUPPORTED,
+                "VT-CNN2 supports MDC_MODE_FP32 and MDC_MODE_BF16 (mode %d not implemented)", mode);
+  }
+  int ndev = 0;
+  MDC_CUDA(cudaGetDeviceCount(&ndev));
+  MDC_REQUIRE(device >= 0 && device < ndev, MDC_ERR_INVALID, "device %d not in [0,%d)", device, ndev);
+  MDC_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  MDC_CUDA(cudaGetDeviceProperties(&prop, device));
+  MDC_REQUIRE(prop.major == 10, MDC_ERR_UNSUPPORTED,
+              "device %d is sm_%d%d; libmdc is built for sm_100a only", device, prop.major, prop.minor);
+  mdc_handle_s* h = new mdc_handle_s();
+  h->model = model_kind;
+  h->F = model_kind == MDC_MODEL_TINY ? filters : 0;
+  h->C = classes;
+  h->mode = mode;
+  h->device = device;
+  h->num_sms = prop.multiProcessorCount;
+  h->dominant_kernel = model_kind == MDC_MODEL_TINY
+                           ? (mode == MDC_MODE_Q612 ? "q612_kernel" : "tiny_f32_kernel")
+                           : (mode == MDC_MODE_FP32 ? "sgemm_bias_act_kernel(conv2)" : "vt_conv_bf16_kernel");
+  *out = h;
+  return MDC_OK;
+}
+
+int mdc_destroy(mdc_handle_t h) {
+  if (!h) return MDC_OK;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  destroy_pipe(h);
+  for (auto& pr : h->prof.pending) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+  DeviceBuffer* bufs[] = {&h->tiny_conv, &h->tiny_dense, &h->tiny_bias, &h->vt_w1, &h->vt_b1, &h->vt_w2,
+                          &h->vt_b2, &h->vt_w3, &h->vt_b3, &h->vt_w4, &h->vt_b4, &h->vt_w2_bf16,
+                          &h->vt_w3_bf16, &h->ws_a1, &h->ws_act, &h->ws_h, &h->q_dense};
+  for (DeviceBuffer* b : bufs) b->release();
+  free(h->tmap_w3);
+  delete h;
+  return MDC_OK;
+}
+
+int mdc_set_option(mdc_handle_t h, int option, int value) {
+  MDC_REQUIRE(h != nullptr, MDC_ERR_INVALID, "null handle");
+  if (option == MDC_OPT_FLATTEN_ORDER) {
+    MDC_REQUIRE(value == 0 || value == 1, MDC_ERR_INVALID, "flatten order must be 0 or 1");
+    h->flatten_order = value;
+    h->packed = false;
+    return MDC_OK;
+  }
+  set_error("unknown option %d", option);
+  return MDC_ERR_INVALID;
+}
+
+int mdc_set_weights_f32(mdc_handle_t h, int tensor_id, const float* host_ptr, size_t count) {
+  MDC_REQUIRE(h != nullptr && host_ptr != nullptr, MDC_ERR_INVALID, "null argument");
+  MDC_REQUIRE(h->mode != MDC_MODE_Q612, MDC_ERR_INVALID,
+              "this handle is in Q6.12 mode: use mdc_set_weights_q612");
+  MDC_REQUIRE(tensor_id >= 0 && tensor_id < 8, MDC_ERR_INVALID, "tensor id %d", tensor_id);
+  const size_t want = tensor_count(h, tensor_id);
+  MDC_REQUIRE(want != 0, MDC_ERR_INVALID, "tensor id %d does not exist for this model", tensor_id);
+  MDC_REQUIRE(count == want, MDC_ERR_INVALID, "tensor %d: expected %zu elements, got %zu", tensor_id, want,
+              count);
+  h->w[tensor_id].assign(host_ptr, host_ptr + count);
+  h->have[tensor_id] = true;
+  h->packed = false;
+  return MDC_OK;
+}
+
+int mdc_set_weights_q612(mdc_handle_t h, const int32_t* conv_tab, const int32_t* dense_bias,
+                         const int32_t* dense_tabs) {
+  MDC_CHECK_HANDLE(h);
+  MDC_REQUIRE(h->model == MDC_MODEL_TINY && h->mode == MDC_MODE_Q612, MDC_ERR_INVALID,
+              "handle is not a TinyCNN2 Q6.12 handle");
+  MDC_REQUIRE(conv_tab && dense_bias && dense_tabs, MDC_ERR_INVALID, "null argument");
+  const int F = h->F, C = h->C;
+  auto in18 = [](int v) { return v >= -(1 << 17) && v < (1 << 17); };
+  for (int i = 0; i < 3 * F; ++i)
+    MDC_REQUIRE(in18(conv_tab[i]), MDC_ERR_INVALID, "conv_tab[%d]=%d is not an 18-bit signed value", i, conv_tab[i]);
+  for (int i = 0; i < C; ++i)
+    MDC_REQUIRE(in18(dense_bias[i]), MDC_ERR_INVALID, "dense_bias[%d]=%d is not an 18-bit signed value", i, dense_bias[i]);
+  const size_t tab = (size_t)129 * F;
+  for (size_t i = 0; i < 2 * C * tab; ++i)
+    MDC_REQUIRE(in18(dense_tabs[i]), MDC_ERR_INVALID, "dense_tabs[%zu]=%d is not an 18-bit signed value", i, dense_tabs[i]);
+  h->q_conv_host.assign(conv_tab, conv_tab + 3 * F);
+  h->q_bias_host.assign(dense_bias, dense_bias + C);
+  // pre-skew: image[f][c][iq][s] = tab[2c+iq][128 f + max(s-1,0)]   (dense_layer, sv:336,351-378)
+  std::vector<int> img((size_t)F * C * 2 * 128);
+  for (int f = 0; f < F; ++f)
+    for (int c = 0; c < C; ++c)
+      for (int iq = 0; iq < 2; ++iq)
+        for (int s = 0; s < 128; ++s)
+          img[(((size_t)f * C + c) * 2 + iq) * 128 + s] =
+              dense_tabs[(size_t)(2 * c + iq) * tab + 128 * f + (s > 0 ? s - 1 : 0)];
+  if (int e = h->q_dense.reserve(img.size() * sizeof(int))) return e;
+  MDC_CUDA(cudaMemcpy(h->q_dense.ptr, img.data(), img.size() * sizeof(int), cudaMemcpyHostToDevice));
+  h->have_q = true;
+  return MDC_OK;
+}
+
+int mdc_predict_f32(mdc_handle_t h, const float* x_dev, int64_t n, float* probs_dev, float* dense_dev,
+                    int32_t* cls_dev, unsigned long long* hist_dev, void* stream) {
+  MDC_CHECK_HANDLE(h);
+  MDC_REQUIRE(h->mode != MDC_MODE_Q612, MDC_ERR_INVALID, "Q6.12 handle: use mdc_predict_q612");
+  MDC_REQUIRE(n >= 0, MDC_ERR_INVALID, "n=%lld < 0", (long long)n);
+  MDC_REQUIRE(n == 0 || x_dev != nullptr, MDC_ERR_INVALID, "x_dev is NULL");
+  MDC_REQUIRE(((uintptr_t)x_dev & 15) == 0, MDC_ERR_INVALID, "x_dev must be 16-byte aligned");
+  if (int e = ensure_packed(h)) return e;
+  return predict_f32_dev(h, x_dev, n, probs_dev, dense_dev, cls_dev, hist_dev, (cudaStream_t)stream);
+}
+
+int mdc_predict_q612(mdc_handle_t h, const int32_t* x_dev, int64_t n, int32_t* out_dev, int32_t* pre_dev,
+                     int32_t* cls_dev, unsigned long long* hist_dev, void* stream) {
+  MDC_CHECK_HANDLE(h);
+  MDC_REQUIRE(h->mode == MDC_MODE_Q612, MDC_ERR_INVALID, "handle is not in Q6.12 mode");
+  MDC_REQUIRE(h->have_q, MDC_ERR_NOT_READY, "ROM tables not set (call mdc_set_weights_q612)");
+  MDC_REQUIRE(n >= 0, MDC_ERR_INVALID, "n=%lld < 0", (long long)n);
+  MDC_REQUIRE(n == 0 || x_dev != nullptr, MDC_ERR_INVALID, "x_dev is NULL");
+  MDC_REQUIRE(((uintptr_t)x_dev & 15) == 0, MDC_ERR_INVALID, "x_dev must be 16-byte aligned");
+  return launch_q612(h, x_dev, n, out_dev, pre_dev, cls_dev, hist_dev, (cudaStream_t)stream);
+}
+
+int mdc_predict_f32_host(mdc_handle_t h, const float* x_host, int64_t n, float* probs_host, float* dense_host,
+                         int32_t* cls_host, unsigned long long* hist_host) {
+  MDC_CHECK_HANDLE(h);
+  MDC_REQUIRE(h->mode != MDC_MODE_Q612, MDC_ERR_INVALID, "Q6.12 handle: use mdc_predict_q612_host");
+  MDC_REQUIRE(n >= 0 && (n == 0 || x_host), MDC_ERR_INVALID, "bad x_host / n");
+  if (int e = ensure_packed(h)) return e;
+  if (n == 0) {
+    if (hist_host) memset(hist_host, 0, h->C * sizeof(unsigned long long));
+    return MDC_OK;
+  }
+  const int64_t chunk = 16384;
+  return run_host_pipeline<float, float, float>(
+      h, x_host, n, probs_host, dense_host, cls_host, hist_host, chunk,
+      [h](const float* x, int64_t m, float* p, float* d, int32_t* c, unsigned long long* hs, cudaStream_t s) {
+        return predict_f32_dev(h, x, m, p, d, c, hs, s);
+      });
+}
+
+int mdc_predict_q612_host(mdc_handle_t h, const int32_t* x_host, int64_t n, int32_t* out_host, int32_t* pre_host,
+                          int32_t* cls_host, unsigned long long* hist_host) {
+  MDC_CHECK_HANDLE(h);
+  MDC_REQUIRE(h->mode == MDC_MODE_Q612, MDC_ERR_INVALID, "handle is not in Q6.12 mode");
+  MDC_REQUIRE(h->have_q, MDC_ERR_NOT_READY, "ROM tables not set (call mdc_set_weights_q612)");
+  MDC_REQUIRE(n >= 0 && (n == 0 || x_host), MDC_ERR_INVALID, "bad x_host / n");
+  if (n == 0) {
+    if (hist_host) memset(hist_host, 0, h->C * sizeof(unsigned long long));
+    return MDC_OK;
+  }
+  const int64_t chunk = 16384;
+  return run_host_pipeline<int32_t, int32_t, int32_t>(
+      h, x_host, n, out_host, pre_host, cls_host, hist_host, chunk,
+      [h](const int32_t* x, int64_t m, int32_t* o, int32_t* p, int32_t* c, unsigned long long* hs, cudaStream_t s) {
+        return launch_q612(h, x, m, o, p, c, hs, s);
+      });
+}
+
+// ---- FWHT ------------------------------------------------------------------------------
+int mdc_fwht_i32(const int32_t* in_dev, int32_t* out_dev, int64_t n_spectra, int log2_npt, int ordering,
+                 void* stream) {
+  MDC_REQUIRE(log2_npt >= 5 && log2_npt <= 13, MDC_ERR_UNSUPPORTED, "log2_npt=%d outside 5..13", log2_npt);
+  MDC_REQUIRE(ordering == MDC_FWHT_NATURAL || ordering == MDC_FWHT_SEQUENCY, MDC_ERR_INVALID, "ordering %d", ordering);
+  MDC_REQUIRE(n_spectra >= 0, MDC_ERR_INVALID, "n_spectra < 0");
+  MDC_REQUIRE(n_spectra == 0 || (in_dev && out_dev), MDC_ERR_INVALID, "null buffer");
+  MDC_REQUIRE((((uintptr_t)in_dev | (uintptr_t)out_dev) & 15) == 0, MDC_ERR_INVALID, "buffers must be 16-byte aligned");
+  return launch_fwht(in_dev, out_dev, n_spectra, log2_npt, ordering, (cudaStream_t)stream);
+}
+
+int mdc_fwht_i32_host(const int32_t* in_host, int32_t* out_host, int64_t n_spectra, int log2_npt, int ordering,
+                      int device) {
+  MDC_REQUIRE(log2_npt >= 5 && log2_npt <= 13, MDC_ERR_UNSUPPORTED, "log2_npt=%d outside 5..13", log2_npt);
+  MDC_REQUIRE(n_spectra >= 0 && (n_spectra == 0 || (in_host && out_host)), MDC_ERR_INVALID, "bad buffers");
+  if (n_spectra == 0) return MDC_OK;
+  MDC_CUDA(cudaSetDevice(device));
+  const size_t N = (size_t)1 << log2_npt;
+  const int64_t chunk = ((int64_t)16 << 20) / (int64_t)(N * 4) > 0 ? ((int64_t)16 << 20) / (int64_t)(N * 4) : 1;
+  constexpr int S = 3;
+  cudaStream_t st[S];
+  void* buf[S];
+  for (int k = 0; k < S; ++k) {
+    MDC_CUDA(cudaStreamCreateWithFlags(&st[k], cudaStreamNonBlocking));
+    MDC_CUDA(cudaMalloc(&buf[k], (size_t)chunk * N * 4));
+  }
+  int rc = MDC_OK;
+  int64_t i = 0;
+  for (int64_t s = 0; s < n_spectra && rc == MDC_OK; s += chunk, ++i) {
+    const int k = (int)(i % S);
+    const int64_t m = (n_spectra - s) < chunk ? (n_spectra - s) : chunk;
+    // a slot's stream is in-order: H2D -> kernel -> D2H; the three slots overlap each other
+    cudaMemcpyAsync(buf[k], in_host + s * N, (size_t)m * N * 4, cudaMemcpyHostToDevice, st[k]);
+    rc = launch_fwht((const int32_t*)buf[k], (int32_t*)buf[k], m, log2_npt, ordering, st[k]);
+    cudaMemcpyAsync(out_host + s * N, buf[k], (size_t)m * N * 4, cudaMemcpyDeviceToHost, st[k]);
+  }
+  for (int k = 0; k < S; ++k) {
+    cudaError_t e = cudaStreamSynchronize(st[k]);
+    if (e != cudaSuccess && rc == MDC_OK) {
+      set_error("fwht host pipeline: %s", cudaGetErrorString(e));
+      rc = MDC_ERR_CUDA;
+    }
+    cudaStreamDestroy(st[k]);
+    cudaFree(buf[k]);
+  }
+  return rc;
+}
+
+int mdc_confusion_i32(const int32_t* true_dev, const int32_t* pred_dev, int64_t n, int classes,
+                      unsigned long long* conf_dev, void* stream) {
+  MDC_REQUIRE(classes >= 1 && classes <= kMaxClasses, MDC_ERR_UNSUPPORTED, "classes=%d", classes);
+  MDC_REQUIRE(n >= 0 && (n == 0 || (true_dev && pred_dev && conf_dev)), MDC_ERR_INVALID, "bad arguments");
+  if (n == 0) return MDC_OK;
+  // at most 2^22 increments of a 32-bit shared counter per block
+  long long blocks = (n + 256LL * 4096 - 1) / (256LL * 4096);
+  if (blocks < 148) blocks = n < 148 * 256 ? 1 : 148;
+  confusion_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(true_dev, pred_dev, n, classes, conf_dev);
+  MDC_CUDA(cudaGetLastError());
+  return MDC_OK;
+}
+
+// ---- introspection ---------------------------------------------------------------------
+int64_t mdc_launch_count(mdc_handle_t h) { return h ? h->launches : 0; }
+
+int mdc_profile_enable(mdc_handle_t h, int on) {
+  MDC_REQUIRE(h != nullptr, MDC_ERR_INVALID, "null handle");
+  h->prof.on = on != 0;
+  return MDC_OK;
+}
+
+int mdc_profile_read(mdc_handle_t h, double* ms_total, int64_t* launches, const char** kernel_name) {
+  MDC_CHECK_HANDLE(h);
+  for (auto& pr : h->prof.pending) {
+    MDC_CUDA(cudaEventSynchronize(pr.second));
+    float ms = 0.f;
+    MDC_CUDA(cudaEventElapsedTime(&ms, pr.first, pr.second));
+    h->prof.ms += ms;
+    h->prof.launches++;
+    cudaEventDestroy(pr.first);
+    cudaEventDestroy(pr.second);
+  }
+  h->prof.pending.clear();
+  if (ms_total) *ms_total = h->prof.ms;
+  if (launches) *launches = h->prof.launches;
+  if (kernel_name) *kernel_name = h->dominant_kernel;
+  h->prof.ms = 0.0;
+  h->prof.launches = 0;
+  return MDC_OK;
+}
+
+}  // extern "C"

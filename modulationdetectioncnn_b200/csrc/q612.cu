@@ -1,0 +1,221 @@
+// Bit-exact integer restatement of the reference's fixed-point datapath as one CUDA kernel.
+//
+// Semantics follow /root/reference/cnn_test_latest1.sv:
+//   signed_mult1 (:642-658)  conv MAC + bias + ReLU       -> conv18()
+//   signed_mult  (:664-675)  dense MAC pair               -> slice36()
+//   conv_layer   (:476-509)  129 positions, zero pad left -> only 0..127 are ever consumed
+//   dense_layer  (:292-348)  acc[c] += slice(...), ROM address 128*f + max(s-1,0)
+//   layers_top   (:173-178)  final ReLU on the 32-bit sums
+//
+// Mapping: one warp per frame.  Lane l owns sample positions s = 4l..4l+3 of both rows, so
+// a frame is two fully coalesced 512 B int4 loads per warp.  The dense ROM entries a lane
+// needs never change (they depend only on s), so for the shipped F=3,C=3 geometry they
+// live in 72 registers for the whole (persistent) kernel; the conv table and biases sit
+// in kernel-parameter constant memory.  Class sums are reduced with REDUX
+// (__reduce_add_sync): 32-bit wrap-around addition is associative, so the reduction order
+// cannot change the result.
+#include "mdc_internal.cuh"
+
+namespace mdc {
+
+struct QParams {
+  int conv[3 * kMaxFilters];
+  int bias[kMaxClasses];
+  int F, C;
+};
+
+__device__ __forceinline__ int wrap18(int v) { return (v << 14) >> 14; }
+
+// {m[35], m[28:12]} of the 36-bit a*b + c*d, as a signed 18-bit value.
+// |a*b + c*d| <= 2^35, exact in 64 bits; bit 35 of the 64-bit two's complement pattern is
+// bit 35 of the value mod 2^36.
+__device__ __forceinline__ int slice36(int a, int b, int c, int d) {
+  long long m = (long long)a * (long long)b + (long long)c * (long long)d;
+  unsigned lo = (unsigned)((unsigned long long)m >> 12);
+  unsigned hi = (unsigned)((unsigned long long)m >> 32);
+  int top = ((int)(hi << 28)) >> 31;                  // 0 or -1 : replicated bit 35
+  return (int)((lo & 0x1FFFFu) | ((unsigned)top & 0xFFFE0000u));
+}
+
+__device__ __forceinline__ int conv18(int a, int w0, int c, int w1, int bias) {
+  int o = wrap18(slice36(a, w0, c, w1) + bias);
+  return o < 0 ? 0 : o;
+}
+
+__device__ __forceinline__ int4 ldg_stream(const int4* p) {
+  int4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+
+// dense image: [f][c][iq][128] with entry s = tab[2c+iq][128 f + max(s-1,0)]  (pre-skewed on host)
+template <int F, int C, bool WREG>
+__global__ void __launch_bounds__(256, 2)
+q612_kernel(const QParams p, const int4* __restrict__ dense4, const int4* __restrict__ x,
+            long long n, int* __restrict__ out, int* __restrict__ pre, int* __restrict__ cls,
+            unsigned long long* __restrict__ hist) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+
+  int4 w[WREG ? F * C * 2 : 1];
+  if (WREG) {
+#pragma unroll
+    for (int i = 0; i < F * C * 2; ++i) w[i] = __ldg(dense4 + i * 32 + lane);
+  }
+  unsigned cnt = 0;
+
+  long long f = warp;
+  int4 xi, xq;
+  if (f < n) {
+    xi = ldg_stream(x + f * 64 + lane);
+    xq = ldg_stream(x + f * 64 + 32 + lane);
+  }
+  while (f < n) {
+    const long long fn = f + nwarps;
+    int4 ni = xi, nq = xq;
+    if (fn < n) {  // prefetch the next frame of this warp
+      ni = ldg_stream(x + fn * 64 + lane);
+      nq = ldg_stream(x + fn * 64 + 32 + lane);
+    }
+    int I[5], Q[5];
+    I[1] = wrap18(xi.x); I[2] = wrap18(xi.y); I[3] = wrap18(xi.z); I[4] = wrap18(xi.w);
+    Q[1] = wrap18(xq.x); Q[2] = wrap18(xq.y); Q[3] = wrap18(xq.z); Q[4] = wrap18(xq.w);
+    I[0] = __shfl_up_sync(0xffffffffu, I[4], 1);
+    Q[0] = __shfl_up_sync(0xffffffffu, Q[4], 1);
+    if (lane == 0) { I[0] = 0; Q[0] = 0; }   // zero padding: ad_in_data[0] (sv:485)
+
+    unsigned acc[C];   // unsigned: wrap-around mod 2^32 is defined behaviour
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc[c] = 0u;
+#pragma unroll
+    for (int k = 0; k < F; ++k) {
+      const int w0 = p.conv[3 * k], w1 = p.conv[3 * k + 1], b = p.conv[3 * k + 2];
+      int yi[4], yq[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        yi[i] = conv18(I[i], w0, I[i + 1], w1, b);
+        yq[i] = conv18(Q[i], w0, Q[i + 1], w1, b);
+      }
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        int4 wi, wq;
+        if (WREG) {
+          wi = w[(k * C + c) * 2];
+          wq = w[(k * C + c) * 2 + 1];
+        } else {
+          wi = __ldg(dense4 + ((k * C + c) * 2) * 32 + lane);
+          wq = __ldg(dense4 + ((k * C + c) * 2 + 1) * 32 + lane);
+        }
+        acc[c] += (unsigned)slice36(yi[0], wi.x, yq[0], wq.x) + (unsigned)slice36(yi[1], wi.y, yq[1], wq.y) +
+                  (unsigned)slice36(yi[2], wi.z, yq[2], wq.z) + (unsigned)slice36(yi[3], wi.w, yq[3], wq.w);
+      }
+    }
+    int best = 0, bestv = 0;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      int s = (int)(__reduce_add_sync(0xffffffffu, acc[c]) + (unsigned)p.bias[c]);
+      int o = s < 0 ? 0 : s;
+      if (lane == 0) {
+        if (pre) pre[f * C + c] = s;
+        if (out) out[f * C + c] = o;
+      }
+      if (c == 0 || o > bestv) { bestv = o; best = c; }
+    }
+    if (lane == 0 && cls) cls[f] = best;
+    cnt += (lane == best);
+    xi = ni; xq = nq;
+    f = fn;
+  }
+  if (hist && lane < C && cnt) atomicAdd(hist + lane, (unsigned long long)cnt);
+}
+
+// Any F<=16, C<=16: runtime loops, ROM entries read through L1.
+__global__ void __launch_bounds__(256)
+q612_generic_kernel(const QParams p, const int4* __restrict__ dense4, const int4* __restrict__ x,
+                    long long n, int* __restrict__ out, int* __restrict__ pre,
+                    int* __restrict__ cls, unsigned long long* __restrict__ hist) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int F = p.F, C = p.C;
+  unsigned cnt = 0;
+  for (long long f = warp; f < n; f += nwarps) {
+    int4 xi = ldg_stream(x + f * 64 + lane), xq = ldg_stream(x + f * 64 + 32 + lane);
+    int I[5], Q[5];
+    I[1] = wrap18(xi.x); I[2] = wrap18(xi.y); I[3] = wrap18(xi.z); I[4] = wrap18(xi.w);
+    Q[1] = wrap18(xq.x); Q[2] = wrap18(xq.y); Q[3] = wrap18(xq.z); Q[4] = wrap18(xq.w);
+    I[0] = __shfl_up_sync(0xffffffffu, I[4], 1);
+    Q[0] = __shfl_up_sync(0xffffffffu, Q[4], 1);
+    if (lane == 0) { I[0] = 0; Q[0] = 0; }
+    unsigned acc[kMaxClasses];
+#pragma unroll
+    for (int c = 0; c < kMaxClasses; ++c) acc[c] = 0u;
+    for (int k = 0; k < F; ++k) {
+      const int w0 = p.conv[3 * k], w1 = p.conv[3 * k + 1], b = p.conv[3 * k + 2];
+      int yi[4], yq[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        yi[i] = conv18(I[i], w0, I[i + 1], w1, b);
+        yq[i] = conv18(Q[i], w0, Q[i + 1], w1, b);
+      }
+#pragma unroll
+      for (int c = 0; c < kMaxClasses; ++c) {
+        if (c < C) {
+          int4 wi = __ldg(dense4 + ((k * C + c) * 2) * 32 + lane);
+          int4 wq = __ldg(dense4 + ((k * C + c) * 2 + 1) * 32 + lane);
+          acc[c] += (unsigned)slice36(yi[0], wi.x, yq[0], wq.x) + (unsigned)slice36(yi[1], wi.y, yq[1], wq.y) +
+                    (unsigned)slice36(yi[2], wi.z, yq[2], wq.z) + (unsigned)slice36(yi[3], wi.w, yq[3], wq.w);
+        }
+      }
+    }
+    int best = 0, bestv = 0;
+#pragma unroll
+    for (int c = 0; c < kMaxClasses; ++c) {
+      if (c < C) {
+        int s = (int)(__reduce_add_sync(0xffffffffu, acc[c]) + (unsigned)p.bias[c]);
+        int o = s < 0 ? 0 : s;
+        if (lane == 0) {
+          if (pre) pre[f * C + c] = s;
+          if (out) out[f * C + c] = o;
+        }
+        if (c == 0 || o > bestv) { bestv = o; best = c; }
+      }
+    }
+    if (lane == 0 && cls) cls[f] = best;
+    cnt += (lane == best);
+  }
+  if (hist && lane < C && cnt) atomicAdd(hist + lane, (unsigned long long)cnt);
+}
+
+int launch_q612(mdc_handle_s* h, const int32_t* x, int64_t n, int32_t* out, int32_t* pre,
+                int32_t* cls, unsigned long long* hist, cudaStream_t stream) {
+  if (n == 0) return MDC_OK;
+  QParams p;
+  const int* conv = h->q_conv_host.data();
+  const int* bias = h->q_bias_host.data();
+  for (int i = 0; i < 3 * kMaxFilters; ++i) p.conv[i] = i < 3 * h->F ? conv[i] : 0;
+  for (int i = 0; i < kMaxClasses; ++i) p.bias[i] = i < h->C ? bias[i] : 0;
+  p.F = h->F;
+  p.C = h->C;
+  const int threads = 256;
+  long long warps_needed = n;
+  long long max_blocks = (long long)h->num_sms * 2 * 4;   // 4 waves of 2 resident CTAs per SM
+  long long blocks = (warps_needed * 32 + threads - 1) / threads;
+  if (blocks > max_blocks) blocks = max_blocks;
+  const int4* d4 = reinterpret_cast<const int4*>(h->q_dense.ptr);
+  const int4* x4 = reinterpret_cast<const int4*>(x);
+  prof_begin(h, stream);
+  if (h->F == 3 && h->C == 3) {
+    q612_kernel<3, 3, true><<<(unsigned)blocks, threads, 0, stream>>>(p, d4, x4, n, out, pre, cls, hist);
+  } else {
+    q612_generic_kernel<<<(unsigned)blocks, threads, 0, stream>>>(p, d4, x4, n, out, pre, cls, hist);
+  }
+  prof_end(h, stream);
+  h->launches++;
+  MDC_CUDA(cudaGetLastError());
+  return MDC_OK;
+}
+
+}  // namespace mdc

@@ -1,0 +1,241 @@
+"""Keras-shaped inference facade over libmdc.so.
+
+Mirrors the call surface the reference uses on its ``Sequential`` model:
+
+* ``model.load_weights(filepath)``            /root/reference/cnn.py:147, CNN.ipynb cell 8
+* ``model.predict(X, batch_size=...)``        cnn.py:198,237; CNN.ipynb cells 12,17,18
+* ``model.evaluate(X, Y, batch_size, verbose)`` cnn.py:154; CNN.ipynb cell 9 (loss only:
+  the model is compiled with ``loss='categorical_crossentropy'`` and no metrics, cnn.py:113)
+* sub-models that stop at an inner layer (``Model(inputs, model.layers[4].output)``,
+  CNN.ipynb cell 17) -> ``predict(..., output="dense")``
+
+Batches are independent in Keras ``predict``; ``batch_size`` only changes the
+chunking and never the result, so it is accepted and ignored (the library picks
+its own chunk size for copy/compute overlap).
+
+Inputs: ``numpy.ndarray`` (host path: H2D/D2H handled by the library) or a CUDA
+``torch.Tensor`` (device path on torch's current stream; returns torch tensors).
+float32 ``(N,2,128)``, row 0 = I, row 1 = Q.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from .h5lite import H5File
+
+__all__ = ["CNN2Model", "tiny_cnn2", "vt_cnn2", "load_model", "read_keras_weights"]
+
+_MODES = {"fp32": _lib.MODE_FP32, "bf16": _lib.MODE_BF16}
+
+
+def _is_torch(x) -> bool:
+    return type(x).__module__.split(".")[0] == "torch"
+
+
+def read_keras_weights(filepath: str) -> List[np.ndarray]:
+    """Weights of a Keras 2.x ``.h5`` in topology order (what ``load_weights`` consumes).
+
+    Handles both full-model files (``/model_weights/...``, as written by
+    ``ModelCheckpoint``, cnn.py:143) and weights-only files (layers at the root).
+    """
+    f = H5File(filepath)
+    root = "/model_weights" if "model_weights" in f.listdir("/") else "/"
+    out: List[np.ndarray] = []
+    for layer in f.attrs(root)["layer_names"]:
+        layer = str(layer)
+        g = f"{root.rstrip('/')}/{layer}"
+        for wn in f.attrs(g).get("weight_names", []):
+            out.append(np.asarray(f.dataset(f"{g}/{wn}"), dtype=np.float32))
+    return out
+
+
+def _config_of(filepath: str) -> Optional[dict]:
+    a = H5File(filepath).attrs("/")
+    return json.loads(a["model_config"]) if "model_config" in a else None
+
+
+class CNN2Model:
+    """TinyCNN2(F,C) or VT-CNN2(C) behind ``load_weights / predict / evaluate``."""
+
+    def __init__(self, kind: str, filters: int = 3, classes: int = 3, mode: str = "fp32",
+                 device: int = 0, flatten: str = "channels_last"):
+        if kind not in ("tiny", "vt"):
+            raise ValueError("kind must be 'tiny' or 'vt'")
+        if mode not in _MODES:
+            raise ValueError(f"mode must be one of {sorted(_MODES)}")
+        if kind == "tiny" and mode != "fp32":
+            raise ValueError("TinyCNN2 float inference is fp32 (integer mode: FixedPointCNN2)")
+        self.kind, self.filters, self.classes, self.mode, self.device = kind, filters, classes, mode, device
+        self.flatten = flatten
+        self._weights: List[np.ndarray] = []
+        self._h = _lib.Handle(_lib.MODEL_TINY if kind == "tiny" else _lib.MODEL_VT, filters, classes,
+                              _MODES[mode], device)
+        if kind == "vt":
+            if flatten not in ("channels_last", "channels_first"):
+                raise ValueError("flatten must be channels_last or channels_first")
+            _lib.check(self._h._lib.mdc_set_option(self._h.ptr, _lib.OPT_FLATTEN_ORDER,
+                                                   int(flatten == "channels_first")))
+
+    # ------------------------------------------------------------------ weights
+    def weight_shapes(self) -> List[tuple]:
+        F, Cn = self.filters, self.classes
+        if self.kind == "tiny":
+            return [(1, 2, 1, F), (F,), (2 * 129 * F, Cn), (Cn,)]
+        return [(1, 3, 1, 256), (256,), (2, 3, 256, 80), (80,), (10560, 256), (256,), (256, Cn), (Cn,)]
+
+    def set_weights(self, weights: Sequence[np.ndarray]) -> None:
+        """Keras ``model.set_weights``: arrays in topology order, Keras layouts."""
+        shapes = self.weight_shapes()
+        if len(weights) != len(shapes):
+            raise ValueError(f"expected {len(shapes)} weight arrays, got {len(weights)}")
+        ids = ([_lib.T_CONV1_K, _lib.T_CONV1_B, _lib.T_DENSE1_K, _lib.T_DENSE1_B] if self.kind == "tiny"
+               else list(range(8)))
+        ws = []
+        for w, shp, tid in zip(weights, shapes, ids):
+            a = np.ascontiguousarray(w, dtype=np.float32)
+            if a.shape != shp:
+                raise ValueError(f"weight {tid}: expected shape {shp}, got {a.shape}")
+            _lib.check(self._h._lib.mdc_set_weights_f32(self._h.ptr, tid, a.ctypes.data, a.size))
+            ws.append(a)
+        self._weights = ws
+
+    def get_weights(self) -> List[np.ndarray]:
+        return [w.copy() for w in self._weights]
+
+    def load_weights(self, filepath: str) -> None:
+        self.set_weights(read_keras_weights(filepath))
+
+    # ------------------------------------------------------------------ inference
+    def _run(self, x, want_probs: bool, want_dense: bool, want_cls: bool, want_hist: bool) -> Dict[str, object]:
+        lib, Cn = self._h._lib, self.classes
+        if _is_torch(x):
+            import torch
+            if not x.is_cuda:
+                raise ValueError("torch inputs must be CUDA tensors (pass numpy for the host path)")
+            xt = x.reshape(-1, 256).to(torch.float32).contiguous()
+            n = xt.shape[0]
+            out: Dict[str, object] = {}
+            with torch.cuda.device(xt.device):
+                if want_probs:
+                    out["probs"] = torch.empty((n, Cn), dtype=torch.float32, device=xt.device)
+                if want_dense:
+                    out["dense"] = torch.empty((n, Cn), dtype=torch.float32, device=xt.device)
+                if want_cls:
+                    out["cls"] = torch.empty((n,), dtype=torch.int32, device=xt.device)
+                if want_hist:
+                    out["hist"] = torch.zeros((Cn,), dtype=torch.int64, device=xt.device)
+                ptr = lambda k: out[k].data_ptr() if k in out else None  # noqa: E731
+                _lib.check(lib.mdc_predict_f32(self._h.ptr, xt.data_ptr(), n, ptr("probs"), ptr("dense"),
+                                               ptr("cls"), ptr("hist"),
+                                               torch.cuda.current_stream(xt.device).cuda_stream))
+            return out
+        xa = np.ascontiguousarray(x, dtype=np.float32).reshape(-1, 256)
+        n = xa.shape[0]
+        out = {}
+        if want_probs:
+            out["probs"] = np.empty((n, Cn), dtype=np.float32)
+        if want_dense:
+            out["dense"] = np.empty((n, Cn), dtype=np.float32)
+        if want_cls:
+            out["cls"] = np.empty((n,), dtype=np.int32)
+        if want_hist:
+            out["hist"] = np.zeros((Cn,), dtype=np.uint64)
+        ptr = lambda k: out[k].ctypes.data if k in out else None  # noqa: E731
+        _lib.check(lib.mdc_predict_f32_host(self._h.ptr, xa.ctypes.data, n, ptr("probs"), ptr("dense"),
+                                            ptr("cls"), ptr("hist")))
+        if want_hist:
+            out["hist"] = out["hist"].astype(np.int64)
+        return out
+
+    def predict(self, x, batch_size: int = 32, verbose: int = 0, output: str = "softmax"):
+        """``output``: "softmax" (the model output), "dense" (last Dense before softmax:
+        Dense+ReLU for TinyCNN2 = ``model2`` of CNN.ipynb cell 17, logits for VT-CNN2),
+        "argmax" (int32 class ids, what cnn.py:209,244 computes per row)."""
+        if output == "softmax":
+            return self._run(x, True, False, False, False)["probs"]
+        if output == "dense":
+            return self._run(x, False, True, False, False)["dense"]
+        if output == "argmax":
+            return self._run(x, False, False, True, False)["cls"]
+        raise ValueError("output must be 'softmax', 'dense' or 'argmax'")
+
+    def predict_classes(self, x):
+        return self.predict(x, output="argmax")
+
+    def class_histogram(self, x):
+        """int64 [C] count of argmax classes (the fused epilogue; one tiny D2H)."""
+        return self._run(x, False, False, False, True)["hist"]
+
+    def evaluate(self, x, y, batch_size: int = 32, verbose: int = 0) -> float:
+        """Mean categorical cross-entropy, Keras semantics (probabilities re-normalised and
+        clipped to [1e-7, 1-1e-7]) - cnn.py:154, CNN.ipynb cell 9."""
+        p = self.predict(x)
+        if _is_torch(p):
+            p = p.cpu().numpy()
+        if _is_torch(y):
+            y = y.cpu().numpy()
+        p = p.astype(np.float64)
+        p = p / p.sum(axis=-1, keepdims=True)
+        p = np.clip(p, 1e-7, 1 - 1e-7)
+        y = np.asarray(y, dtype=np.float64).reshape(p.shape)
+        return float(-(y * np.log(p)).sum(axis=-1).mean())
+
+    # ------------------------------------------------------------------ misc
+    def summary(self) -> str:
+        if self.kind == "tiny":
+            F, Cn = self.filters, self.classes
+            rows = [("Reshape", (2, 128, 1), 0), ("ZeroPadding2D", (2, 130, 1), 0),
+                    ("Conv2D+ReLU", (2, 129, F), 3 * F), ("Flatten", (258 * F,), 0),
+                    ("Dense+ReLU", (Cn,), 258 * F * Cn + Cn), ("Softmax", (Cn,), 0)]
+        else:
+            Cn = self.classes
+            rows = [("Reshape", (1, 2, 128), 0), ("ZeroPadding2D", (1, 2, 132), 0),
+                    ("Conv2D 1x3 +ReLU", (256, 2, 130), 1024), ("ZeroPadding2D", (256, 2, 134), 0),
+                    ("Conv2D 2x3 +ReLU", (80, 1, 132), 122960), ("Flatten", (10560,), 0),
+                    ("Dense+ReLU", (256,), 2703616), ("Dense", (Cn,), 256 * Cn + Cn), ("Softmax", (Cn,), 0)]
+        lines = [f"{n:<20}{str(s):<18}{p:>10}" for n, s, p in rows]
+        lines.append(f"Total params: {sum(p for _, _, p in rows)}")
+        text = "\n".join(lines)
+        print(text)
+        return text
+
+    def launch_count(self) -> int:
+        return self._h.launch_count()
+
+    def close(self) -> None:
+        self._h.close()
+
+
+def tiny_cnn2(filters: int = 3, classes: int = 3, device: int = 0) -> CNN2Model:
+    """The net of CNN.ipynb cell 6 (filters=3) / cnn.py-era checkpoint (filters=10)."""
+    return CNN2Model("tiny", filters, classes, "fp32", device)
+
+
+def vt_cnn2(classes: int = 11, mode: str = "bf16", device: int = 0, flatten: str = "channels_last") -> CNN2Model:
+    """VT-CNN2 of the example notebook (:231-243)."""
+    return CNN2Model("vt", 0, classes, mode, device, flatten)
+
+
+def load_model(filepath: str, device: int = 0, mode: str = "fp32") -> CNN2Model:
+    """Keras ``load_model``: topology from the ``model_config`` embedded in the ``.h5``
+    (SURVEY.md Appendix B.1), then ``load_weights``."""
+    cfg = _config_of(filepath)
+    if cfg is None:
+        raise ValueError(f"{filepath}: no model_config (weights-only file): build the model, then load_weights")
+    layers = cfg["config"]["layers"]
+    convs = [l["config"] for l in layers if l["class_name"] in ("Conv2D", "Convolution2D")]
+    denses = [l["config"] for l in layers if l["class_name"] == "Dense"]
+    if len(convs) == 1 and len(denses) == 1 and tuple(convs[0]["kernel_size"]) == (1, 2):
+        m = tiny_cnn2(int(convs[0]["filters"]), int(denses[0]["units"]), device)
+    elif len(convs) == 2 and len(denses) == 2 and int(convs[0]["filters"]) == 256 and int(convs[1]["filters"]) == 80:
+        fmt = convs[0].get("data_format", "channels_last")
+        m = vt_cnn2(int(denses[1]["units"]), mode, device, fmt)
+    else:
+        raise ValueError(f"{filepath}: topology is neither TinyCNN2 nor VT-CNN2")
+    m.load_weights(filepath)
+    return m

@@ -1,0 +1,106 @@
+"""Integer (SystemVerilog-exact) CNN2: the fixed-point datapath behind a model-like facade.
+
+Stands in for one reset-to-done run of ``layers_top`` per frame
+(/root/reference/cnn_test_latest1.sv:144-209) fed by ``test_input``/``test_table``
+(:71-142).  Weights are the literal ROM/table contents of the ``*.Weights.txt`` files
+(never re-quantised checkpoints: the deployed ROMs contain hand edits).
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Sequence
+
+import numpy as np
+
+from . import _lib, svtext
+from .svtext import QWeights
+
+__all__ = ["FixedPointCNN2"]
+
+
+def _is_torch(x) -> bool:
+    return type(x).__module__.split(".")[0] == "torch"
+
+
+class FixedPointCNN2:
+    def __init__(self, filters: int = 3, classes: int = 3, device: int = 0):
+        self.filters, self.classes, self.device = filters, classes, device
+        self._h = _lib.Handle(_lib.MODEL_TINY, filters, classes, _lib.MODE_Q612, device)
+        self.tables: Optional[QWeights] = None
+
+    # ---- weights
+    def set_tables(self, qw: QWeights) -> None:
+        qw.validate()
+        if qw.filters != self.filters or qw.classes != self.classes:
+            raise ValueError(f"tables are F={qw.filters},C={qw.classes}; model is F={self.filters},C={self.classes}")
+        ct = np.ascontiguousarray(qw.conv_tab, dtype=np.int32)
+        db = np.ascontiguousarray(qw.dense_bias, dtype=np.int32)
+        dt = np.ascontiguousarray(qw.dense_tabs, dtype=np.int32)
+        _lib.check(self._h._lib.mdc_set_weights_q612(self._h.ptr, ct.ctypes.data, db.ctypes.data, dt.ctypes.data))
+        self.tables = qw
+
+    def load_weights(self, filepath: str, *, conv_from: Optional[str] = None,
+                     dense_bias: Optional[Sequence[int]] = None, overwidth: str = "verilog") -> None:
+        """Load a ``*.Weights.txt`` file (see :func:`svtext.load_qweights`)."""
+        self.set_tables(svtext.load_qweights(filepath, conv_from=conv_from, dense_bias=dense_bias,
+                                             classes=self.classes, overwidth=overwidth))
+
+    # ---- inference
+    def _run(self, x, want: Sequence[str]) -> Dict[str, object]:
+        lib, Cn = self._h._lib, self.classes
+        if _is_torch(x):
+            import torch
+            if not x.is_cuda:
+                raise ValueError("torch inputs must be CUDA tensors (pass numpy for the host path)")
+            xt = x.reshape(-1, 256).to(torch.int32).contiguous()
+            n = xt.shape[0]
+            out: Dict[str, object] = {}
+            with torch.cuda.device(xt.device):
+                for k in want:
+                    if k == "hist":
+                        out[k] = torch.zeros((Cn,), dtype=torch.int64, device=xt.device)
+                    elif k == "cls":
+                        out[k] = torch.empty((n,), dtype=torch.int32, device=xt.device)
+                    else:
+                        out[k] = torch.empty((n, Cn), dtype=torch.int32, device=xt.device)
+                ptr = lambda k: out[k].data_ptr() if k in out else None  # noqa: E731
+                _lib.check(lib.mdc_predict_q612(self._h.ptr, xt.data_ptr(), n, ptr("out"), ptr("pre"), ptr("cls"),
+                                                ptr("hist"), torch.cuda.current_stream(xt.device).cuda_stream))
+            return out
+        xa = np.ascontiguousarray(x, dtype=np.int32).reshape(-1, 256)
+        n = xa.shape[0]
+        out = {}
+        for k in want:
+            if k == "hist":
+                out[k] = np.zeros((Cn,), dtype=np.uint64)
+            elif k == "cls":
+                out[k] = np.empty((n,), dtype=np.int32)
+            else:
+                out[k] = np.empty((n, Cn), dtype=np.int32)
+        ptr = lambda k: out[k].ctypes.data if k in out else None  # noqa: E731
+        _lib.check(lib.mdc_predict_q612_host(self._h.ptr, xa.ctypes.data, n, ptr("out"), ptr("pre"), ptr("cls"),
+                                             ptr("hist")))
+        if "hist" in out:
+            out["hist"] = out["hist"].astype(np.int64)
+        return out
+
+    def predict(self, x, output: str = "out"):
+        """x int32 [N,256] (0-127 I, 128-255 Q; values are wrapped to 18 bits like a sized
+        Verilog literal).  ``output``: "out" (``out_data``, ReLU'd Q.12 int32 [N,C]),
+        "pre" (``pre_out_data``), "argmax"."""
+        key = {"out": "out", "pre": "pre", "argmax": "cls"}.get(output)
+        if key is None:
+            raise ValueError("output must be 'out', 'pre' or 'argmax'")
+        return self._run(x, [key])[key]
+
+    def class_histogram(self, x):
+        return self._run(x, ["hist"])["hist"]
+
+    def predict_file(self, path: str, overwidth: str = "verilog") -> np.ndarray:
+        """Run every 256-entry vector of a ``*testData*.txt`` file."""
+        return self.predict(svtext.load_vectors(path, overwidth))
+
+    def launch_count(self) -> int:
+        return self._h.launch_count()
+
+    def close(self) -> None:
+        self._h.close()

@@ -1,0 +1,64 @@
+"""N>1 host logic on CPU: world_size-2 gloo run of the frame sharding + histogram all-reduce."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from modulationdetectioncnn_b200.dist import shard_range
+
+
+def test_shard_range_partitions():
+    for n in (0, 1, 7, 65536, 10 ** 9):
+        for w in (1, 2, 3, 4, 8):
+            parts = [shard_range(n, r, w) for r in range(w)]
+            assert parts[0][0] == 0 and parts[-1][1] == n
+            assert all(parts[i][1] == parts[i + 1][0] for i in range(w - 1))
+            sizes = [b - a for a, b in parts]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_range(10, 2, 2)
+
+
+def _worker(rank, world, port, n, q):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank),
+                      MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch.distributed as dist
+    from modulationdetectioncnn_b200.dist import allreduce_histogram, init_process_group, shard_range
+    from oracle import sv_datapath as sv
+    import json
+    init_process_group("gloo")
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "qweights.npz"))
+    w = (g["A_conv_tab"], g["A_dense_bias"], g["A_dense_tabs"])
+    # every rank builds the same global stream, classifies only its shard (oracle stands in for the GPU)
+    x = np.trunc(np.random.Generator(np.random.Philox(2015)).normal(0, 32, (n, 256))).astype(np.int32)
+    lo, hi = shard_range(n, rank, world)
+    cls = sv.forward(x[lo:hi], *w).argmax(-1)
+    hist = np.bincount(cls, minlength=3).astype(np.int64)
+    total = allreduce_histogram(hist)
+    q.put((rank, hist.tolist(), total.tolist()))
+    dist.destroy_process_group()
+
+
+def test_histogram_allreduce_world2():
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    n = 1001
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    res.sort()
+    total = np.array(res[0][1]) + np.array(res[1][1])
+    assert res[0][2] == res[1][2] == total.tolist()
+    assert total.sum() == n                              # histogram conservation
+    from oracle import sv_datapath as sv
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "qweights.npz"))
+    x = np.trunc(np.random.Generator(np.random.Philox(2015)).normal(0, 32, (n, 256))).astype(np.int32)
+    full = np.bincount(sv.forward(x, g["A_conv_tab"], g["A_dense_bias"], g["A_dense_tabs"]).argmax(-1), minlength=3)
+    assert full.tolist() == total.tolist()               # sharded == unsharded
