@@ -1,0 +1,429 @@
+#!/usr/bin/env python
+"""Benchmark of the CNN2 hot path (BASELINE.json metric: CNN2 I/Q frames/s, 2x128 frames).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+N>1 is launched by torchrun (one rank per GPU, NCCL).  A "step" is one pass of the hot path
+over one batch of 65,536 synthetic frames per GPU (BASELINE.json configs[1]: the 11-class
+VT-CNN2 stack on synthetic 2x128 I/Q, batch 65536).  Frames are independent, so ranks share
+nothing but the final class-histogram all-reduce: scaling is weak, value = frames of all
+ranks / max-over-ranks device time.
+
+One JSON line on stdout (rank 0).  Keys beyond the base contract:
+  roofline      dominant kernel (fused conv1+conv2 implicit GEMM): algorithmic FLOPs / CUDA-event time
+  cpu_baseline  the CPU stand-in for the reference's Keras/TF predict (oracle/cnn2_torch_cpu.py)
+  e2e           same metric through the public API with pinned HOST buffers (H2D + D2H inside)
+  other_paths   the HBM-bound rows of SURVEY section 8d (integer SV-exact, TinyCNN2 fp32, FWHT),
+                each with its own roofline
+`--impl reference` times only the CPU stand-in (rank 0), on bounded samples of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BATCH = 65536                       # frames per GPU per step (configs[1])
+N_INPUT_BUFFERS = 4                 # 4 x 64 MiB = 256 MiB of distinct inputs > 126 MB L2
+VT_FLOP_PER_FRAME = 38_252_032      # 2 x 19,126,016 MAC (whole net)
+VT_CONV_FLOP_PER_FRAME = 2 * (199_680 + 16_220_160)   # conv1 + conv2: the dominant (fused) kernel
+METRIC = "cnn2_frames_per_sec"
+UNIT = "frames/s"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._t = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._dev = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._dev, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self._nv = None
+
+    def _loop(self):
+        nv = self._nv
+        names = {
+            getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self._dev, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._dev)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
+    def __enter__(self):
+        if self._nv:
+            self._t = threading.Thread(target=self._loop, daemon=True)
+            self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._t:
+            self._t.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml_unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------
+def cpu_vt_baseline(weights, budget_s: float = 12.0):
+    """Frames/s of the torch-CPU stand-in on a bounded sample sized for ~budget_s of CPU work."""
+    import torch
+    from oracle.cnn2_torch_cpu import VTCNN2Cpu
+    from modulationdetectioncnn_b200 import synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    m = VTCNN2Cpu(*weights)
+    x = synth.iq_frames(256, seed=2016)
+    m.predict(x[:64], batch_size=64)                     # warm-up
+    t = time.perf_counter()
+    m.predict(x, batch_size=256)
+    rate = 256 / (time.perf_counter() - t)
+    n = int(min(BATCH, max(512, rate * budget_s))) // 256 * 256
+    x = synth.iq_frames(n, seed=2016)
+    t = time.perf_counter()
+    m.predict(x, batch_size=256)
+    dt = time.perf_counter() - t
+    return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n} frames of the {BATCH}-frame batch, torch-CPU (oneDNN/MKL) VT-CNN2 fp32, batch 256",
+            "seconds": dt}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    from modulationdetectioncnn_b200 import synth
+    import torch
+    from oracle.cnn2_torch_cpu import VTCNN2Cpu
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    m = VTCNN2Cpu(*synth.vt_cnn2_weights(11, 1602))
+    x = synth.iq_frames(256, seed=2016)
+    m.predict(x[:64], batch_size=64)
+    t = time.perf_counter()
+    m.predict(x, batch_size=256)
+    rate = 256 / (time.perf_counter() - t)
+    total = args.steps + args.warmup
+    n = int(min(BATCH, max(256, rate * 120.0 / total))) // 256 * 256      # whole run <= ~2 min
+    x = synth.iq_frames(n, seed=2016)
+    for _ in range(args.warmup):
+        m.predict(x, batch_size=256)
+    t = time.perf_counter()
+    for _ in range(args.steps):
+        m.predict(x, batch_size=256)
+    dt = time.perf_counter() - t
+    v = n * args.steps / dt
+    sample = f"{n} frames per step (bounded sample of the {BATCH}-frame batch), torch-CPU stand-in for Keras/TF-CPU predict"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "VT-CNN2 11-class (C2b), synthetic 2x128 I/Q", "frames_per_step": n,
+                   "weights": "synthetic Philox(1602)", "note": "Keras/TensorFlow are not installable here; "
+                   "torch-CPU runs the same layer stack on all host cores"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ------------------------------------------------------------------------------------------
+def time_device(fn, steps, warmup, torch, dist_on):
+    """W warm-up calls, then K calls bracketed by barrier + synchronize; CUDA-event ms, max over ranks."""
+    import torch.distributed as dist
+    for i in range(warmup):
+        fn(i)
+    torch.cuda.synchronize()
+    if dist_on:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        fn(warmup + i)
+    e1.record()
+    torch.cuda.synchronize()
+    if dist_on:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    if dist_on:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
+
+
+def time_host(fn, steps, warmup, torch, dist_on):
+    import torch.distributed as dist
+    for i in range(warmup):
+        fn(i)
+    torch.cuda.synchronize()
+    if dist_on:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        fn(warmup + i)
+    torch.cuda.synchronize()
+    ms = (time.perf_counter() - t0) * 1e3
+    if dist_on:
+        dist.barrier()
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
+
+
+def hbm_path(name, handle_like, call_dev, call_host, bytes_per_unit, units, unit_name, peaks, torch, steps=5, warmup=3,
+             h2d=0, d2h=0, extra=None):
+    """One HBM-bound path: device-resident throughput + roofline + e2e."""
+    ms = time_device(lambda i: call_dev(i), steps, warmup, torch, False)
+    per = ms / steps
+    achieved = bytes_per_unit * units / (per * 1e-3) / 1e9
+    out = {"path": name, "value": units / (per * 1e-3), "unit": unit_name, "ms_per_step": per,
+           "units_per_step": units,
+           "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                        "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
+                        "algorithmic_bytes_per_unit": bytes_per_unit}}
+    if call_host is not None:
+        hms = time_host(lambda i: call_host(i), 3, 1, torch, False) / 3
+        out["e2e"] = {"value": units / (hms * 1e-3), "unit": unit_name, "h2d_bytes_per_step": h2d,
+                      "d2h_bytes_per_step": d2h}
+    if extra:
+        out.update(extra)
+    return out
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from modulationdetectioncnn_b200 import synth
+    from modulationdetectioncnn_b200.dist import allreduce_histogram, init_process_group, rank_world
+    from modulationdetectioncnn_b200.model import tiny_cnn2, vt_cnn2
+    from modulationdetectioncnn_b200.qmodel import FixedPointCNN2
+    from modulationdetectioncnn_b200.svtext import QWeights
+    from modulationdetectioncnn_b200.fwht import fwht
+
+    rank, world, local = rank_world()
+    dist_on = world > 1
+    if dist_on:
+        init_process_group("nccl")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    peaks = load_peaks()
+
+    # ---------------- headline: VT-CNN2 (C2b), batch 65536 per GPU
+    weights = synth.vt_cnn2_weights(11, 1602)
+    mode = args.mode
+    model = vt_cnn2(11, mode=mode, device=local)
+    model.set_weights(weights)
+    batch = args.batch
+    gen = torch.Generator(device=dev).manual_seed(2016 + rank)
+    xs = [torch.randn((batch, 2, 128), generator=gen, device=dev, dtype=torch.float32).mul_(2.0 ** -7)
+          for _ in range(N_INPUT_BUFFERS)]
+    probs = torch.empty((batch, 11), dtype=torch.float32, device=dev)
+    hist = torch.zeros((11,), dtype=torch.int64, device=dev)
+    lib, h = model._h._lib, model._h
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    from modulationdetectioncnn_b200 import _lib
+
+    def step_dev(i):
+        x = xs[i % N_INPUT_BUFFERS]
+        _lib.check(lib.mdc_predict_f32(h.ptr, x.data_ptr(), batch, probs.data_ptr(), None, None, hist.data_ptr(), stream))
+
+    step_dev(0)
+    torch.cuda.synchronize()
+    hist.zero_()
+    launches0 = None
+    h.profile_enable(False)
+    for i in range(args.warmup):
+        step_dev(i)
+    torch.cuda.synchronize()
+    h.profile_enable(True)
+    h.profile_read()
+    launches0 = h.launch_count()
+    hist.zero_()
+    with ClockSampler(local) as clk:
+        ms = time_device(step_dev, args.steps, 0, torch, dist_on)
+    launches = h.launch_count() - launches0
+    kms, klaunches, kname = h.profile_read()
+    h.profile_enable(False)
+    total_hist = allreduce_histogram(hist)
+    frames_all = batch * args.steps * world
+    assert int(total_hist.sum()) == frames_all, (total_hist, frames_all)     # conservation over ranks
+    value = frames_all / (ms * 1e-3)
+
+    tensor = mode == "bf16"
+    flops_launch = VT_CONV_FLOP_PER_FRAME * batch * args.steps / max(klaunches, 1)
+    k_avg_ms = kms / max(klaunches, 1)
+    achieved = flops_launch / (k_avg_ms * 1e-3) / 1e12 if klaunches else None
+    peak = peaks["bf16_tflops_sustained"] if tensor else None
+    roofline = {"bound": "tensor", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": (achieved / peak) if (achieved and peak) else None, "traffic": None,
+                "peak_source": peaks["source"] + (" (bf16 sustained)" if tensor else ""),
+                "launches": klaunches, "avg_launch_ms": k_avg_ms,
+                "algorithmic_flop_per_frame": VT_CONV_FLOP_PER_FRAME,
+                "kernel_share_of_step": kms / ms if ms else None,
+                "whole_net_tflops": VT_FLOP_PER_FRAME * batch * args.steps / (ms * 1e-3) / 1e12}
+    if not tensor:
+        roofline["note"] = "fp32 CUDA-core parity mode: no tensor-pipe peak applies; frac is null"
+
+    # ---------------- e2e through the public API, pinned host buffers
+    xh = [torch.randn((batch, 2, 128), dtype=torch.float32).mul_(2.0 ** -7).pin_memory() for _ in range(2)]
+    xh_np = [t.numpy() for t in xh]
+    ph = torch.empty((batch, 11), dtype=torch.float32).pin_memory()
+    ph_np = ph.numpy()
+    hh = np.zeros(11, dtype=np.uint64)
+
+    def step_host(i):
+        x = xh_np[i % 2]
+        _lib.check(lib.mdc_predict_f32_host(h.ptr, x.ctypes.data, batch, ph_np.ctypes.data, None, None, hh.ctypes.data))
+
+    e2e_steps = max(2, min(args.steps, 10))
+    hms = time_host(step_host, e2e_steps, 2, torch, dist_on)
+    e2e = {"value": batch * e2e_steps * world / (hms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": batch * 1024,
+           "d2h_bytes_per_step": batch * 11 * 4 + 11 * 8, "steps": e2e_steps,
+           "api": "mdc_predict_f32_host (what CNN2Model.predict(numpy) calls)"}
+
+    result = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16" if tensor else "f32", "data": "synthetic",
+        "config": {"workload": "VT-CNN2 11-class (BASELINE configs[1] / SURVEY C2b), 2x128 I/Q frames",
+                   "frames_per_gpu_per_step": batch, "weights": "synthetic Glorot/He, Philox(1602)",
+                   "input": "N(0, 2^-7) float32, torch.Generator(seed 2016+rank)", "mode": mode,
+                   "l2": f"{N_INPUT_BUFFERS} distinct input buffers rotated ({N_INPUT_BUFFERS * batch * 1024 >> 20} MiB > 126 MB L2)",
+                   "parallelism": f"frame-sharded dp{world}, one NCCL all-reduce of int64[11] histogram"},
+        "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk.summary(),
+    }
+
+    # ---------------- rank 0, N=1: CPU baseline + the HBM-bound paths
+    if rank == 0 and world == 1 and not args.skip_other:
+        result["cpu_baseline"] = cpu_vt_baseline(weights)
+        result["other_paths"] = other_paths(torch, dev, peaks, _lib)
+    if rank == 0:
+        print(json.dumps(result))
+    if dist_on:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def other_paths(torch, dev, peaks, _lib):
+    from modulationdetectioncnn_b200 import synth
+    from modulationdetectioncnn_b200.model import tiny_cnn2
+    from modulationdetectioncnn_b200.qmodel import FixedPointCNN2
+    from modulationdetectioncnn_b200.svtext import QWeights
+    out = []
+    g = np.load(os.path.join(ROOT, "tests", "golden", "qweights.npz"))
+    hw = np.load(os.path.join(ROOT, "tests", "golden", "h5_weights.npz"))
+    gen = torch.Generator(device=dev).manual_seed(2015)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+
+    # C1: integer SV-exact, N = 2^21 frames (2 GiB > L2)
+    n = 1 << 21
+    xq = torch.randn((n, 256), generator=gen, device=dev).mul_(32).trunc_().to(torch.int32)
+    qm = FixedPointCNN2(3, 3, dev.index)
+    qm.set_tables(QWeights(g["A_conv_tab"], g["A_dense_bias"], g["A_dense_tabs"]))
+    oq = torch.empty((n, 3), dtype=torch.int32, device=dev)
+    hq = torch.zeros(3, dtype=torch.int64, device=dev)
+    nh = 1 << 18
+    xq_h = torch.from_numpy(synth.q612_frames(nh)).pin_memory().numpy()
+    oq_h = np.empty((nh, 3), dtype=np.int32)
+    out.append(hbm_path(
+        "q612_sv_exact (C1, weight set A)", qm,
+        lambda i: _lib.check(qm._h._lib.mdc_predict_q612(qm._h.ptr, xq.data_ptr(), n, oq.data_ptr(), None, None, hq.data_ptr(), stream)),
+        lambda i: _lib.check(qm._h._lib.mdc_predict_q612_host(qm._h.ptr, xq_h.ctypes.data, nh, oq_h.ctypes.data, None, None, None)),
+        1036, n, UNIT, peaks, torch, h2d=nh * 1024, d2h=nh * 12,
+        extra={"dtype": "int18/36 in int32/int64", "e2e_units_per_step": nh}))
+    del xq, oq
+
+    # C2a / C3: TinyCNN2 fp32 from the real checkpoints
+    n = 1 << 21
+    xf = torch.randn((n, 2, 128), generator=gen, device=dev).mul_(2.0 ** -7)
+    pf = torch.empty((n, 3), dtype=torch.float32, device=dev)
+    xf_h = torch.from_numpy(synth.iq_frames(nh)).pin_memory().numpy()
+    pf_h = np.empty((nh, 3), dtype=np.float32)
+    for tag, label, flop in (("A_3conv", "tiny_f32 F=3 (C3, 3conv checkpoint)", 7740), ("E_f10", "tiny_f32 F=10 (C2a, convmodrecnets_CNN2_0.5)", 25800)):
+        w = [hw[f"{tag}_{k}"] for k in ("conv_k", "conv_b", "dense_k", "dense_b")]
+        tm = tiny_cnn2(w[0].shape[-1], 3, dev.index)
+        tm.set_weights(w)
+        out.append(hbm_path(
+            label, tm,
+            lambda i: _lib.check(tm._h._lib.mdc_predict_f32(tm._h.ptr, xf.data_ptr(), n, pf.data_ptr(), None, None, None, stream)),
+            lambda i: _lib.check(tm._h._lib.mdc_predict_f32_host(tm._h.ptr, xf_h.ctypes.data, nh, pf_h.ctypes.data, None, None, None)),
+            1036, n, UNIT, peaks, torch, h2d=nh * 1024, d2h=nh * 12,
+            extra={"dtype": "f32", "flop_per_frame": flop, "e2e_units_per_step": nh}))
+    del xf, pf
+
+    # C4: FWHT 1024-pt, 2^18 spectra (1 GiB in + 1 GiB out)
+    s = 1 << 18
+    xw = torch.randn((s, 1024), generator=gen, device=dev).mul_(32).trunc_().to(torch.int32)
+    yw = torch.empty_like(xw)
+    lib = _lib.load()
+    sh = 1 << 15
+    xw_h = torch.from_numpy(synth.q612_frames(sh * 4).reshape(sh, 1024)).pin_memory().numpy()
+    yw_h = torch.empty((sh, 1024), dtype=torch.int32).pin_memory().numpy()
+    out.append(hbm_path(
+        "fwht_1024 int32 (C4)", None,
+        lambda i: _lib.check(lib.mdc_fwht_i32(xw.data_ptr(), yw.data_ptr(), s, 10, 0, stream)),
+        lambda i: _lib.check(lib.mdc_fwht_i32_host(xw_h.ctypes.data, yw_h.ctypes.data, sh, 10, 0, dev.index)),
+        8192, s, "spectra/s", peaks, torch, h2d=sh * 4096, d2h=sh * 4096,
+        extra={"dtype": "int32", "realtime_requirement_spectra_per_s": 9.6e6, "e2e_units_per_step": sh}))
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default=os.environ.get("MDC_BENCH_MODE", "bf16"), choices=["bf16", "fp32"])
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--skip-other", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,114 @@
+"""GPU parity: the integer (SystemVerilog-exact) kernel through the C ABI vs the oracle.  Bit-exact."""
+import numpy as np
+import pytest
+
+from conftest import philox
+
+pytestmark = pytest.mark.gpu
+
+
+def _model(qsets, k):
+    from modulationdetectioncnn_b200.qmodel import FixedPointCNN2
+    from modulationdetectioncnn_b200.svtext import QWeights
+    m = FixedPointCNN2(3, 3)
+    m.set_tables(QWeights(*[a.copy() for a in qsets[k]]))
+    return m
+
+
+@pytest.mark.parametrize("k", list("ABCD"))
+def test_fixture_vectors_all_weight_sets(golden, qsets, k):
+    from oracle import sv_datapath as sv
+    V = golden["vectors"]["vectors"]
+    m = _model(qsets, k)
+    pre = m.predict(V, output="pre")
+    out = m.predict(V, output="out")
+    assert pre.tolist() == golden["int_goldens"]["pre"][k]
+    assert np.array_equal(out, sv.forward(V, *qsets[k]))
+    assert np.array_equal(m.predict(V, output="argmax"), out.argmax(-1))
+
+
+def test_testbench_vector(golden, qsets):
+    tb = golden["int_goldens"]["testbench_vector"]
+    v = np.zeros((1, 256), dtype=np.int32)
+    for a, val in tb["nonzero"].items():
+        v[0, int(a)] = val
+    m = _model(qsets, "A")
+    assert m.predict(v, output="pre")[0].tolist() == tb["pre"]
+    assert m.predict(v, output="out")[0].tolist() == tb["out"]
+
+
+@pytest.mark.parametrize("k", list("ABCD"))
+def test_fuzz_full_range_and_fixture_like(qsets, k):
+    from oracle import sv_datapath as sv
+    g = philox(2016)
+    full = g.integers(-(1 << 17), 1 << 17, (3000, 256)).astype(np.int32)      # C1(iii): wrap paths
+    small = np.trunc(philox(2015).normal(0, 32, (5000, 256))).astype(np.int32)  # C1(ii)
+    edge = np.array([[-(1 << 17)] * 256, [(1 << 17) - 1] * 256, [0] * 256], dtype=np.int32)
+    m = _model(qsets, k)
+    for x in (full, small, edge):
+        assert np.array_equal(m.predict(x, output="pre"), sv.forward_pre(x, *qsets[k]))
+
+
+def test_random_tables_full_range():
+    """Random full-range ROMs (incl. -2^17): every wrap path of slice/bias-add/accumulate."""
+    from modulationdetectioncnn_b200.qmodel import FixedPointCNN2
+    from modulationdetectioncnn_b200.svtext import QWeights
+    from oracle import sv_datapath as sv
+    g = philox(5)
+    for F, C in ((3, 3), (10, 3), (4, 2), (1, 1), (16, 16)):
+        conv = g.integers(-(1 << 17), 1 << 17, 3 * F).astype(np.int32)
+        bias = g.integers(-(1 << 17), 1 << 17, C).astype(np.int32)
+        tabs = g.integers(-(1 << 17), 1 << 17, (2 * C, 129 * F)).astype(np.int32)
+        tabs[0, 0] = -(1 << 17)
+        x = g.integers(-(1 << 17), 1 << 17, (700, 256)).astype(np.int32)
+        x[0] = -(1 << 17)
+        m = FixedPointCNN2(F, C)
+        m.set_tables(QWeights(conv, bias, tabs))
+        assert np.array_equal(m.predict(x, output="pre"), sv.forward_pre(x, conv, bias, tabs)), (F, C)
+        assert np.array_equal(m.predict(x, output="out"), sv.forward(x, conv, bias, tabs)), (F, C)
+
+
+def test_inputs_are_wrapped_to_18_bits(qsets):
+    from oracle import sv_datapath as sv
+    g = philox(9)
+    x = g.integers(-(1 << 31), 1 << 31, (64, 256)).astype(np.int32)
+    w18 = ((x.astype(np.int64) + (1 << 17)) % (1 << 18) - (1 << 17)).astype(np.int32)
+    m = _model(qsets, "A")
+    assert np.array_equal(m.predict(x, output="pre"), sv.forward_pre(w18, *qsets["A"]))
+
+
+def test_empty_ragged_and_device_path(qsets):
+    import torch
+    from oracle import sv_datapath as sv
+    m = _model(qsets, "A")
+    assert m.predict(np.zeros((0, 256), dtype=np.int32)).shape == (0, 3)
+    assert m.class_histogram(np.zeros((0, 256), dtype=np.int32)).tolist() == [0, 0, 0]
+    for n in (1, 31, 33, 16385, 40001):          # around warp / host-chunk boundaries
+        x = np.trunc(philox(n).normal(0, 300, (n, 256))).astype(np.int32)
+        want = sv.forward(x, *qsets["A"])
+        assert np.array_equal(m.predict(x), want)
+        xt = torch.from_numpy(x).cuda()
+        assert np.array_equal(m.predict(xt).cpu().numpy(), want)
+        h = m.class_histogram(xt).cpu().numpy()
+        assert h.tolist() == np.bincount(want.argmax(-1), minlength=3).tolist()
+        assert m.class_histogram(x).tolist() == h.tolist()
+
+
+def test_full_size_properties(qsets):
+    """BASELINE size (N = 2^22 frames, 4 GiB): properties that need no oracle, plus a sampled check."""
+    import torch
+    from oracle import sv_datapath as sv
+    n = 1 << 22
+    gen = torch.Generator(device="cuda").manual_seed(2015)
+    x = torch.randn((n, 256), generator=gen, device="cuda").mul_(32).trunc_().to(torch.int32)
+    m = _model(qsets, "A")
+    out = m.predict(x)
+    hist = m.class_histogram(x).cpu().numpy()
+    assert int(hist.sum()) == n                                           # conservation
+    assert torch.equal(out, m.predict(x))                                 # deterministic
+    assert hist.tolist() == torch.bincount(m.predict(x, output="argmax").long(), minlength=3).cpu().tolist()
+    perm = torch.randperm(n, device="cuda", generator=gen)[: 1 << 16]
+    assert torch.equal(m.predict(x[perm]), out[perm])                     # frames are independent
+    idx = torch.arange(0, n, n // 4096, device="cuda")[:4096]
+    assert np.array_equal(out[idx].cpu().numpy(), sv.forward(x[idx].cpu().numpy(), *qsets["A"]))
+    assert (out >= 0).all()

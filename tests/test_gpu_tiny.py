@@ -1,0 +1,92 @@
+"""GPU parity: TinyCNN2 fp32 through the Keras-shaped facade vs the fp64 oracle and the Keras KATs.
+Tolerance (north_star): 1e-5 relative."""
+import numpy as np
+import pytest
+
+from conftest import philox
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5
+
+
+def _model(w):
+    from modulationdetectioncnn_b200.model import tiny_cnn2
+    m = tiny_cnn2(filters=w[0].shape[-1], classes=w[3].shape[0])
+    m.set_weights(w)
+    return m
+
+
+def test_keras_recorded_output(golden, h5w):
+    kat = golden["kat"]
+    x = np.array(kat["cell18_frame"], dtype=np.float32).reshape(1, 2, 128)
+    m = _model(h5w["A_3conv"])
+    z = m.predict(x, output="dense")[0]                      # model2 of CNN.ipynb cell 17
+    np.testing.assert_allclose(z, kat["keras_dense_64samples"], rtol=RTOL)
+    p = m.predict(x)[0]
+    e = np.exp(np.array(kat["keras_dense_64samples"]) - max(kat["keras_dense_64samples"]))
+    np.testing.assert_allclose(p, e / e.sum(), rtol=RTOL)
+
+
+@pytest.mark.parametrize("tag", ["A_3conv", "B_2conv", "C_5conv", "D_4conv", "E_f10"])
+def test_checkpoints_vs_oracle(h5w, tag):
+    from oracle import cnn2_float as cf
+    w = h5w[tag]
+    x = philox(2016).normal(0, 2 ** -7, (4099, 2, 128)).astype(np.float32)      # C2a input law
+    x[:3] *= 300                                                                  # large activations too
+    m = _model(w)
+    z = m.predict(x, output="dense")
+    zo = cf.tiny_cnn2_forward(x, *w, output="dense")
+    np.testing.assert_allclose(z, zo, rtol=RTOL, atol=1e-6)
+    p = m.predict(x, batch_size=1024)
+    po = cf.tiny_cnn2_forward(x, *w)
+    np.testing.assert_allclose(p, po, rtol=RTOL, atol=1e-7)
+    np.testing.assert_allclose(p.sum(-1), 1, atol=1e-6)
+    cls = m.predict_classes(x)
+    margin = np.sort(zo, axis=-1)
+    clear = (margin[:, -1] - margin[:, -2]) > 1e-4
+    assert np.array_equal(cls[clear], zo.argmax(-1)[clear])
+    assert np.array_equal(cls, z.argmax(-1))                  # fused argmax == argmax of its own output
+    assert m.class_histogram(x).tolist() == np.bincount(cls, minlength=3).tolist()
+
+
+def test_load_model_from_golden_like_geometries():
+    """Generic (non-specialised) geometries go through the runtime-shape kernel."""
+    from modulationdetectioncnn_b200.model import tiny_cnn2
+    from oracle import cnn2_float as cf
+    g = philox(11)
+    for F, C in ((1, 1), (4, 2), (7, 11), (16, 16)):
+        w = [g.normal(0, 1, (1, 2, 1, F)).astype(np.float32), g.normal(0, 0.1, F).astype(np.float32),
+             g.normal(0, 0.05, (258 * F, C)).astype(np.float32), g.normal(0, 0.1, C).astype(np.float32)]
+        x = g.normal(0, 1, (257, 2, 128)).astype(np.float32)
+        m = tiny_cnn2(F, C)
+        m.set_weights(w)
+        np.testing.assert_allclose(m.predict(x, output="dense"), cf.tiny_cnn2_forward(x, *w, output="dense"),
+                                   rtol=RTOL, atol=1e-5)
+        np.testing.assert_allclose(m.predict(x), cf.tiny_cnn2_forward(x, *w), rtol=1e-4, atol=1e-6)
+
+
+def test_evaluate_and_device_path(h5w):
+    import torch
+    from oracle import cnn2_float as cf
+    w = h5w["A_3conv"]
+    g = philox(3)
+    x = g.normal(0, 2 ** -7, (2048, 2, 128)).astype(np.float32)
+    y = np.eye(3)[g.integers(0, 3, 2048)]
+    m = _model(w)
+    loss = m.evaluate(x, y, batch_size=1024, verbose=0)
+    assert abs(loss - cf.categorical_crossentropy(cf.tiny_cnn2_forward(x, *w), y)) < 1e-5
+    xt = torch.from_numpy(x).cuda()
+    pt = m.predict(xt)
+    assert pt.is_cuda and np.allclose(pt.cpu().numpy(), m.predict(x), rtol=0, atol=0)   # same kernel, same bits
+    assert m.predict(np.zeros((0, 2, 128), np.float32)).shape == (0, 3)
+    with pytest.raises(ValueError):
+        m.set_weights(w[:3])
+
+
+def test_reads_reference_h5_when_present(reference_dir, h5w):
+    import os
+    from modulationdetectioncnn_b200.model import load_model
+    m = load_model(os.path.join(reference_dir, "3convmodrecnets_CNN2_0.5.wts.h5"))
+    assert (m.kind, m.filters, m.classes) == ("tiny", 3, 3)
+    x = philox(1).normal(0, 2 ** -7, (64, 2, 128)).astype(np.float32)
+    assert np.array_equal(m.predict(x), _model(h5w["A_3conv"]).predict(x))

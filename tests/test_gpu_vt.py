@@ -1,0 +1,83 @@
+"""GPU parity: VT-CNN2 through the facade vs the fp64 oracle (synthetic seeded weights -
+the reference ships none; parity unpinned)."""
+import numpy as np
+import pytest
+
+from conftest import philox
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def vt():
+    from oracle import cnn2_float as cf
+    w = cf.vt_cnn2_init(classes=11, seed=1602)
+    x = philox(2016).normal(0, 2 ** -7, (300, 2, 128)).astype(np.float32)
+    x[:8] *= 64            # some frames with O(1) samples
+    ref = {k: cf.vt_cnn2_forward(x, **w, output=k) for k in ("logits", "softmax")}
+    return w, x, ref
+
+
+def _wlist(w):
+    return [w[k] for k in ("w1", "b1", "w2", "b2", "w3", "b3", "w4", "b4")]
+
+
+def test_fp32_mode_within_1e5(vt):
+    from modulationdetectioncnn_b200.model import vt_cnn2
+    w, x, ref = vt
+    m = vt_cnn2(11, mode="fp32")
+    m.set_weights(_wlist(w))
+    z = m.predict(x, output="dense")
+    scale = np.abs(ref["logits"]).max(axis=-1, keepdims=True)
+    assert np.max(np.abs(z - ref["logits"]) / scale) < 1e-5
+    p = m.predict(x)
+    np.testing.assert_allclose(p, ref["softmax"], rtol=1e-4, atol=1e-7)
+    np.testing.assert_allclose(p.sum(-1), 1, atol=1e-6)
+    assert np.array_equal(m.predict_classes(x), z.argmax(-1))
+    assert m.class_histogram(x).sum() == x.shape[0]
+
+
+def test_fp32_channels_first_flatten(vt):
+    from modulationdetectioncnn_b200.model import vt_cnn2
+    w, x, ref = vt
+    w3cf = w["w3"].reshape(132, 80, 256).transpose(1, 0, 2).reshape(10560, 256).copy()
+    m = vt_cnn2(11, mode="fp32", flatten="channels_first")
+    ws = _wlist(w)
+    ws[4] = w3cf
+    m.set_weights(ws)
+    z = m.predict(x[:64], output="dense")
+    scale = np.abs(ref["logits"][:64]).max(axis=-1, keepdims=True)
+    assert np.max(np.abs(z - ref["logits"][:64]) / scale) < 1e-5
+
+
+def test_bf16_mode_tolerance(vt):
+    """bf16 operands, fp32 accumulate: logits within 2e-2 of the largest logit; argmax agrees
+    wherever the oracle's top-2 margin exceeds that error."""
+    from modulationdetectioncnn_b200.model import vt_cnn2
+    w, x, ref = vt
+    m = vt_cnn2(11, mode="bf16")
+    m.set_weights(_wlist(w))
+    z = m.predict(x, output="dense")
+    scale = np.abs(ref["logits"]).max(axis=-1, keepdims=True)
+    err = np.abs(z - ref["logits"]) / scale
+    assert err.max() < 2e-2, err.max()
+    p = m.predict(x)
+    assert np.abs(p - ref["softmax"]).max() < 2e-2
+    srt = np.sort(ref["logits"], axis=-1)
+    clear = (srt[:, -1] - srt[:, -2]) > 4e-2 * scale[:, 0]
+    assert np.array_equal(m.predict_classes(x)[clear], ref["logits"].argmax(-1)[clear])
+
+
+def test_bf16_ragged_sizes_and_determinism(vt):
+    import torch
+    from modulationdetectioncnn_b200.model import vt_cnn2
+    w, x, ref = vt
+    m = vt_cnn2(11, mode="bf16")
+    m.set_weights(_wlist(w))
+    full = m.predict(x, output="dense")
+    for n in (1, 2, 5, 127, 129, 300):
+        part = m.predict(x[:n], output="dense")
+        assert np.array_equal(part, full[:n]), n          # frames are independent: same bits
+    xt = torch.from_numpy(x).cuda()
+    assert np.array_equal(m.predict(xt, output="dense").cpu().numpy(), full)
+    assert m.predict(np.zeros((0, 2, 128), np.float32)).shape == (0, 11)
