@@ -211,7 +211,7 @@ def time_host(fn, steps, warmup, torch, dist_on):
 
 
 def hbm_path(name, handle_like, call_dev, call_host, bytes_per_unit, units, unit_name, peaks, torch, steps=5, warmup=3,
-             h2d=0, d2h=0, extra=None):
+             h2d=0, d2h=0, extra=None, host_units=None):
     """One HBM-bound path: device-resident throughput + roofline + e2e."""
     ms = time_device(lambda i: call_dev(i), steps, warmup, torch, False)
     per = ms / steps
@@ -223,8 +223,8 @@ def hbm_path(name, handle_like, call_dev, call_host, bytes_per_unit, units, unit
                         "algorithmic_bytes_per_unit": bytes_per_unit}}
     if call_host is not None:
         hms = time_host(lambda i: call_host(i), 3, 1, torch, False) / 3
-        out["e2e"] = {"value": units / (hms * 1e-3), "unit": unit_name, "h2d_bytes_per_step": h2d,
-                      "d2h_bytes_per_step": d2h}
+        out["e2e"] = {"value": host_units / (hms * 1e-3), "unit": unit_name, "h2d_bytes_per_step": h2d,
+                      "d2h_bytes_per_step": d2h, "units_per_step": host_units}
     if extra:
         out.update(extra)
     return out
@@ -370,7 +370,7 @@ def other_paths(torch, dev, peaks, _lib):
         lambda i: _lib.check(qm._h._lib.mdc_predict_q612(qm._h.ptr, xq.data_ptr(), n, oq.data_ptr(), None, None, hq.data_ptr(), stream)),
         lambda i: _lib.check(qm._h._lib.mdc_predict_q612_host(qm._h.ptr, xq_h.ctypes.data, nh, oq_h.ctypes.data, None, None, None)),
         1036, n, UNIT, peaks, torch, h2d=nh * 1024, d2h=nh * 12,
-        extra={"dtype": "int18/36 in int32/int64", "e2e_units_per_step": nh}))
+        extra={"dtype": "int18/36 in int32/int64"}, host_units=nh))
     del xq, oq
 
     # C2a / C3: TinyCNN2 fp32 from the real checkpoints
@@ -388,7 +388,7 @@ def other_paths(torch, dev, peaks, _lib):
             lambda i: _lib.check(tm._h._lib.mdc_predict_f32(tm._h.ptr, xf.data_ptr(), n, pf.data_ptr(), None, None, None, stream)),
             lambda i: _lib.check(tm._h._lib.mdc_predict_f32_host(tm._h.ptr, xf_h.ctypes.data, nh, pf_h.ctypes.data, None, None, None)),
             1036, n, UNIT, peaks, torch, h2d=nh * 1024, d2h=nh * 12,
-            extra={"dtype": "f32", "flop_per_frame": flop, "e2e_units_per_step": nh}))
+            extra={"dtype": "f32", "flop_per_frame": flop}, host_units=nh))
     del xf, pf
 
     # C4: FWHT 1024-pt, 2^18 spectra (1 GiB in + 1 GiB out)
@@ -404,7 +404,7 @@ def other_paths(torch, dev, peaks, _lib):
         lambda i: _lib.check(lib.mdc_fwht_i32(xw.data_ptr(), yw.data_ptr(), s, 10, 0, stream)),
         lambda i: _lib.check(lib.mdc_fwht_i32_host(xw_h.ctypes.data, yw_h.ctypes.data, sh, 10, 0, dev.index)),
         8192, s, "spectra/s", peaks, torch, h2d=sh * 4096, d2h=sh * 4096,
-        extra={"dtype": "int32", "realtime_requirement_spectra_per_s": 9.6e6, "e2e_units_per_step": sh}))
+        extra={"dtype": "int32", "realtime_requirement_spectra_per_s": 9.6e6}, host_units=sh))
     return out
 
 
