@@ -24,7 +24,7 @@ EXPORTS = [
     "mdc_create", "mdc_destroy", "mdc_set_option", "mdc_set_weights_f32", "mdc_set_weights_q612",
     "mdc_predict_f32", "mdc_predict_f32_host", "mdc_predict_q612", "mdc_predict_q612_host",
     "mdc_fwht_i32", "mdc_fwht_i32_host", "mdc_confusion_i32", "mdc_last_error", "mdc_version",
-    "mdc_launch_count", "mdc_profile_enable", "mdc_profile_read",
+    "mdc_launch_count", "mdc_profile_enable", "mdc_profile_read", "mdc_debug_read",
 ]
 
 
@@ -65,6 +65,7 @@ def load() -> C.CDLL:
         "mdc_launch_count": (i64, [vp]),
         "mdc_profile_enable": (i32, [vp, i32]),
         "mdc_profile_read": (i32, [vp, C.POINTER(C.c_double), C.POINTER(i64), C.POINTER(C.c_char_p)]),
+        "mdc_debug_read": (i32, [vp, i32, vp, sz, C.POINTER(sz)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

@@ -473,4 +473,16 @@ int mdc_profile_read(mdc_handle_t h, double* ms_total, int64_t* launches, const 
   return MDC_OK;
 }
 
+int mdc_debug_read(mdc_handle_t h, int what, void* host_dst, size_t bytes, size_t* copied) {
+  MDC_CHECK_HANDLE(h);
+  MDC_REQUIRE(host_dst != nullptr, MDC_ERR_INVALID, "null destination");
+  MDC_REQUIRE(what == 0 || what == 1, MDC_ERR_INVALID, "unknown intermediate %d", what);
+  const DeviceBuffer& b = what == 0 ? h->ws_act : h->ws_h;
+  const size_t nb = bytes < b.bytes ? bytes : b.bytes;
+  MDC_CUDA(cudaDeviceSynchronize());
+  if (nb) MDC_CUDA(cudaMemcpy(host_dst, b.ptr, nb, cudaMemcpyDeviceToHost));
+  if (copied) *copied = nb;
+  return MDC_OK;
+}
+
 }  // extern "C"

@@ -1,7 +1,563 @@
-// placeholder until the tcgen05 path lands (replaced in a later commit)
+// VT-CNN2 forward on the sm_100a tensor cores (MDC_MODE_BF16): bf16 operands, fp32 accumulate.
+//
+// Layer stack: /root/reference/examples-master/modulation_recognition/
+// RML2016.10a_VTCNN2_example.ipynb:231-243 (shapes :194-216); Dropout = identity.
+//
+// Two persistent, warp-specialised tcgen05 kernels plus the small fp32 head of vt_f32.cu:
+//
+//   vt_conv_bf16_kernel   conv1 (1x3, 256 ch, fp32 FMA on CUDA cores, produced straight into the
+//                         shared-memory A operand) -> conv2 (2x3, 80 ch) as an implicit GEMM
+//                         M = frames*132, N = 80, K = 3 taps x 512 (row,channel) -> +bias, ReLU
+//                         -> bf16 activations act[frames*132][80]   (== Keras channels_last flatten)
+//   vt_dense_bf16_kernel  act[frames][10560] x W3 -> +bias, ReLU -> h[frames][256] fp32
+//                         (TMA 128B-swizzled tiles, M = 256 per CTA, N = 256, K = 10560)
+//   vt_head_kernel        Dense(C) + softmax + argmax + histogram (fp32, vt_f32.cu)
+//
+// The implicit GEMM keeps conv1's padded output positions as GEMM rows: frame f owns rows
+// [132 f, 132 f + 134) of one long activation "tape" whose rows 132 f and 132 f + 1 are the zero
+// padding shared by frame f-1 (right pad) and frame f (left pad).  conv2 output row R needs tape
+// rows R, R+1, R+2, so with the no-swizzle K-major operand layout (8-channel groups, rows 16 B
+// apart) tap j is the SAME shared-memory image with the descriptor start address moved by 16 j
+// bytes - conv1 activations are produced once and read by three MMAs.
+#include <cudaTypedefs.h>
+
 #include "mdc_internal.cuh"
+#include "sm100.cuh"
+
 namespace mdc {
-int pack_vt_bf16(mdc_handle_s*) { set_error("MDC_MODE_BF16 not built yet"); return MDC_ERR_UNSUPPORTED; }
-int launch_vt_bf16(mdc_handle_s*, const float*, int64_t, float*, float*, int32_t*, unsigned long long*, cudaStream_t) {
-  set_error("MDC_MODE_BF16 not built yet"); return MDC_ERR_UNSUPPORTED; }
+using namespace sm100;
+
+int launch_vt_head(mdc_handle_s* h, const float* hbuf, int64_t n, float* probs, float* dense,
+                   int32_t* cls, unsigned long long* hist, cudaStream_t stream);
+int pack_vt_small(mdc_handle_s* h);
+void vt_permute_w3(const mdc_handle_s* h, std::vector<float>& out);
+
+// ------------------------------------------------------------------------------------------
+// conv kernel geometry
+constexpr int kNT = 6;                    // accumulator tiles (128 rows x 80 cols) per super-tile
+constexpr int kTapeRows = 128 * kNT;      // 768 tape rows staged per super-tile
+constexpr int kOutRows = kTapeRows - 2;   // 766 conv2 rows produced per super-tile (2-row halo)
+constexpr int kKC = 16;                   // K channels per pipeline chunk (one UMMA K step)
+constexpr int kGroups = kKC / 8;          // 8-channel groups per chunk
+constexpr int kChunks = 512 / kKC;        // chunks per super-tile (K = 2 rows x 256 channels)
+constexpr int kStages = 5;
+constexpr int kALbo = kTapeRows * 16;     // bytes between 8-channel groups of the A image
+constexpr int kASlot = kGroups * kALbo;   // 24,576
+constexpr int kBLbo = 80 * 16;            // bytes between 8-channel groups of the B image
+constexpr int kBSlot = 3 * kGroups * kBLbo;   // 7,680: [tap][group][80][8]
+constexpr int kXFrames = 7;               // frames a super-tile's tape rows can touch
+constexpr int kOutTile = 128 * 160;       // one 128 x 80 bf16 output tile
+constexpr int kConvThreads = 14 * 32;     // TMA, MMA, 4 epilogue, 8 producer warps
+constexpr int kProdWarp0 = 6;
+constexpr int kProdWarps = 8;
+
+struct ConvSmem {
+  static constexpr int a = 0;
+  static constexpr int b = a + kStages * kASlot;
+  static constexpr int xs = b + kStages * kBSlot;
+  static constexpr int out = xs + kXFrames * 1024;
+  static constexpr int w1 = out + 2 * kOutTile;       // 32 groups x 128 B
+  static constexpr int b2 = w1 + 32 * 128;            // 80 floats
+  static constexpr int bars = b2 + 320;
+  // full[S], empty[S], x_full, x_empty, tmem_full[NT], tmem_empty[NT]
+  static constexpr int nbars = 2 * kStages + 2 + 2 * kNT;
+  static constexpr int tmem_slot = bars + nbars * 8;
+  static constexpr int total = tmem_slot + 16;
+};
+static_assert(ConvSmem::total <= 232448, "conv kernel shared memory exceeds 227 KB");
+
+__device__ __forceinline__ uint64_t pack_dup(float v) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %1};" : "=l"(d) : "f"(v));
+  return d;
 }
+__device__ __forceinline__ uint64_t fma2_u(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint32_t relu_pack(uint64_t v) {   // {lo, hi} fp32 -> bf16x2, ReLU
+  float lo, hi;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+  return cvt_relu_bf16x2(hi, lo);
+}
+
+__global__ void __launch_bounds__(kConvThreads, 1)
+vt_conv_bf16_kernel(const float* __restrict__ x, long long n, const uint8_t* __restrict__ w1img,
+                    const float* __restrict__ b2g, const uint8_t* __restrict__ w2img,
+                    __nv_bfloat16* __restrict__ act, long long num_st) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ConvSmem::bars);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kStages;
+  uint64_t* x_full = bars + 2 * kStages;
+  uint64_t* x_empty = x_full + 1;
+  uint64_t* tmem_full = x_empty + 1;
+  uint64_t* tmem_empty = tmem_full + kNT;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + ConvSmem::tmem_slot);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long total_rows = n * 132;
+
+  // ---- one-time setup
+  for (int i = tid; i < 32 * 128 / 16; i += kConvThreads)
+    reinterpret_cast<uint4*>(smem + ConvSmem::w1)[i] = reinterpret_cast<const uint4*>(w1img)[i];
+  for (int i = tid; i < 80; i += kConvThreads) reinterpret_cast<float*>(smem + ConvSmem::b2)[i] = b2g[i];
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full[s], kProdWarps + 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(x_full, 1);
+    mbar_init(x_empty, kProdWarps);
+    for (int t = 0; t < kNT; ++t) {
+      mbar_init(&tmem_full[t], 1);
+      mbar_init(&tmem_empty[t], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<512>(tmem_slot);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA: frames of the super-tile + the W2 chunk stream
+    if (lane == 0) {
+      uint32_t it = 0, k = 0;
+      for (long long st = blockIdx.x; st < num_st; st += gridDim.x, ++k) {
+        const long long f0 = (st * kOutRows) / 132;
+        const long long left = n - f0;
+        const uint32_t nf = left < kXFrames ? (uint32_t)left : (uint32_t)kXFrames;
+        mbar_wait(x_empty, (k & 1) ^ 1);
+        mbar_arrive_expect_tx(x_full, nf * 1024);
+        bulk_g2s(smem + ConvSmem::xs, x + f0 * 256, nf * 1024, x_full);
+        for (int c = 0; c < kChunks; ++c, ++it) {
+          const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&full[s], kBSlot);
+          bulk_g2s(smem + ConvSmem::b + s * kBSlot, w2img + (size_t)c * kBSlot, kBSlot, &full[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (one thread)
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, 80);
+      const uint32_t a_base = smem_u32(smem + ConvSmem::a), b_base = smem_u32(smem + ConvSmem::b);
+      uint32_t it = 0, k = 0;
+      for (long long st = blockIdx.x; st < num_st; st += gridDim.x, ++k) {
+        for (int c = 0; c < kChunks; ++c, ++it) {
+          const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+          mbar_wait(&full[s], ph);
+          tc_fence_after_sync();
+          const uint32_t a_slot = a_base + s * kASlot, b_slot = b_base + s * kBSlot;
+#pragma unroll
+          for (int t = 0; t < kNT; ++t) {
+            if (c == 0) {
+              mbar_wait(&tmem_empty[t], (k & 1) ^ 1);
+              tc_fence_after_sync();
+            }
+#pragma unroll
+            for (int g2 = 0; g2 < kKC / 16; ++g2) {
+#pragma unroll
+              for (int j = 0; j < 3; ++j) {
+                const uint64_t ad = make_smem_desc(a_slot + (2 * g2) * kALbo + (128 * t + j) * 16, kALbo, 128, 0);
+                const uint64_t bd = make_smem_desc(b_slot + (j * kGroups + 2 * g2) * kBLbo, kBLbo, 128, 0);
+                mma_bf16_ss(tmem + t * 80, ad, bd, idesc, (c | g2 | j) != 0);
+              }
+            }
+            if (c == kChunks - 1) mma_commit(&tmem_full[t]);
+          }
+          mma_commit(&empty[s]);
+        }
+      }
+    }
+  } else if (warp < kProdWarp0) {
+    // ================= epilogue: TMEM -> +bias, ReLU, bf16 -> smem tile -> bulk store
+    const int q = warp & 3;                      // TMEM lane quarter this warp may read
+    const bool leader = (warp == 2 && lane == 0);
+    const float* b2s = reinterpret_cast<const float*>(smem + ConvSmem::b2);
+    uint32_t k = 0, tile_ctr = 0;
+    for (long long st = blockIdx.x; st < num_st; st += gridDim.x, ++k) {
+      const long long r0 = st * kOutRows;
+#pragma unroll 1
+      for (int t = 0; t < kNT; ++t, ++tile_ctr) {
+        uint8_t* obuf = smem + ConvSmem::out + (tile_ctr & 1) * kOutTile;
+        if (leader) bulk_wait_read<1>();          // the store issued two tiles ago has drained obuf
+        named_bar_sync(1, 128);
+        mbar_wait(&tmem_full[t], k & 1);
+        tc_fence_after_sync();
+        uint32_t v[80];
+#pragma unroll
+        for (int cc = 0; cc < 5; ++cc) {
+          uint32_t(&vv)[16] = *reinterpret_cast<uint32_t(*)[16]>(&v[cc * 16]);
+          tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + t * 80 + cc * 16, vv);
+        }
+        tmem_ld_wait();
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[t]);
+        uint8_t* orow = obuf + (q * 32 + lane) * 160;
+#pragma unroll
+        for (int c8 = 0; c8 < 10; ++c8) {
+          uint32_t p[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int col = c8 * 8 + 2 * e;
+            p[e] = cvt_relu_bf16x2(__uint_as_float(v[col + 1]) + b2s[col + 1], __uint_as_float(v[col]) + b2s[col]);
+          }
+          *reinterpret_cast<uint4*>(orow + c8 * 16) = make_uint4(p[0], p[1], p[2], p[3]);
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(2, 128);
+        if (leader) {
+          const long long row_lo = r0 + 128 * t;
+          long long rows = kOutRows - 128 * t;
+          if (rows > 128) rows = 128;
+          if (row_lo + rows > total_rows) rows = total_rows - row_lo;
+          if (rows > 0) bulk_s2g(act + row_lo * 80, obuf, (uint32_t)rows * 160);
+          bulk_commit();
+        }
+      }
+    }
+    if (leader) bulk_wait<0>();
+  } else {
+    // ================= conv1 producers: fp32 FMA -> ReLU -> bf16 -> A operand image
+    const int pw = warp - kProdWarp0;
+    const float* xs = reinterpret_cast<const float*>(smem + ConvSmem::xs);
+    const ulonglong2* w1s = reinterpret_cast<const ulonglong2*>(smem + ConvSmem::w1);
+    uint32_t it = 0, k = 0;
+    for (long long st = blockIdx.x; st < num_st; st += gridDim.x, ++k) {
+      const long long t0 = st * kOutRows;          // first tape row of this super-tile
+      const long long f0 = t0 / 132;
+      mbar_wait(x_full, k & 1);
+      // this thread owns tape rows (pw + 8 i) * 32 + lane, i = 0..2, for the whole super-tile
+      uint64_t xd[3][2][3];
+      uint32_t mask[3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const long long tp = t0 + (pw + kProdWarps * i) * 32 + lane;
+        const long long f = tp / 132;
+        const int p = (int)(tp - f * 132);
+        const bool valid = (p >= 2) && (f < n);
+        mask[i] = valid ? 0xFFFFFFFFu : 0u;
+        const float* xf = xs + (f - f0) * 256;
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            const int xi = p - 4 + j;               // conv1 position p-2 reads x[p-4 .. p-2]
+            const float xv = (valid && xi >= 0 && xi < 128) ? xf[r * 128 + xi] : 0.f;
+            xd[i][r][j] = pack_dup(xv);
+          }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(x_empty);
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+#pragma unroll 1
+        for (int cr = 0; cr < kChunks / 2; ++cr, ++it) {
+          const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          uint8_t* aslot = smem + ConvSmem::a + s * kASlot;
+#pragma unroll
+          for (int g = 0; g < kGroups; ++g) {
+            const ulonglong2* wg = w1s + (cr * kGroups + g) * 8;
+            const ulonglong2 wa0 = wg[0], wa1 = wg[1], wb0 = wg[2], wb1 = wg[3], wc0 = wg[4], wc1 = wg[5],
+                             bb0 = wg[6], bb1 = wg[7];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+              const uint64_t x0 = xd[i][r][0], x1 = xd[i][r][1], x2 = xd[i][r][2];
+              uint64_t a0 = fma2_u(x0, wa0.x, bb0.x), a1 = fma2_u(x0, wa0.y, bb0.y);
+              uint64_t a2 = fma2_u(x0, wa1.x, bb1.x), a3 = fma2_u(x0, wa1.y, bb1.y);
+              a0 = fma2_u(x1, wb0.x, a0); a1 = fma2_u(x1, wb0.y, a1);
+              a2 = fma2_u(x1, wb1.x, a2); a3 = fma2_u(x1, wb1.y, a3);
+              a0 = fma2_u(x2, wc0.x, a0); a1 = fma2_u(x2, wc0.y, a1);
+              a2 = fma2_u(x2, wc1.x, a2); a3 = fma2_u(x2, wc1.y, a3);
+              const uint32_t m = mask[i];
+              const uint4 o = make_uint4(relu_pack(a0) & m, relu_pack(a1) & m, relu_pack(a2) & m, relu_pack(a3) & m);
+              *reinterpret_cast<uint4*>(aslot + g * kALbo + ((pw + kProdWarps * i) * 32 + lane) * 16) = o;
+            }
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&full[s]);
+        }
+      }
+    }
+  }
+
+  // ---- teardown
+  __syncwarp();
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
+// ------------------------------------------------------------------------------------------
+// dense1: h = relu(act W3 + b3).  A = act [frames][10560] bf16 (K-major), B = W3^T [256][10560].
+constexpr int kDM = 256;                  // frames per CTA tile (two M = 128 accumulators)
+constexpr int kDK = 64;                   // K elements per stage (128 B swizzled rows)
+constexpr int kDStages = 3;
+constexpr int kDKBlocks = kVtFlat / kDK;  // 165
+constexpr int kDTileBytes = kDM * 128;    // 32 KB (A and B tiles are the same size)
+constexpr int kDenseThreads = 10 * 32;    // TMA, MMA, 8 epilogue warps
+static_assert(kVtFlat % kDK == 0, "K must tile");
+
+struct DenseSmem {
+  static constexpr int a = 0;
+  static constexpr int b = a + kDStages * kDTileBytes;
+  static constexpr int b3 = b + kDStages * kDTileBytes;
+  static constexpr int bars = b3 + 1024;
+  static constexpr int nbars = 2 * kDStages + 2;
+  static constexpr int tmem_slot = bars + nbars * 8;
+  static constexpr int total = tmem_slot + 16 + 1024;   // + slack for the 1024 B alignment
+};
+static_assert(DenseSmem::total <= 232448, "dense kernel shared memory exceeds 227 KB");
+
+__global__ void __launch_bounds__(kDenseThreads, 1)
+vt_dense_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                     const float* __restrict__ b3g, float* __restrict__ hbuf, long long n, int num_tiles) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DenseSmem::bars);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kDStages;
+  uint64_t* tmem_full = bars + 2 * kDStages;
+  uint64_t* tmem_empty = tmem_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + DenseSmem::tmem_slot);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  for (int i = tid; i < 256; i += kDenseThreads) reinterpret_cast<float*>(smem + DenseSmem::b3)[i] = b3g[i];
+  if (tid == 0) {
+    for (int s = 0; s < kDStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    mbar_init(tmem_empty, 8);
+    fence_barrier_init();
+    prefetch_tensormap(&map_a);
+    prefetch_tensormap(&map_b);
+  }
+  if (warp == 0) tmem_alloc<512>(tmem_slot);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int kb = 0; kb < kDKBlocks; ++kb, ++it) {
+          const uint32_t s = it % kDStages, ph = (it / kDStages) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&full[s], 2 * kDTileBytes);
+          tma_load_2d(smem + DenseSmem::a + s * kDTileBytes, &map_a, kb * kDK, tile * kDM, &full[s]);
+          tma_load_2d(smem + DenseSmem::b + s * kDTileBytes, &map_b, kb * kDK, 0, &full[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, 256);
+      const uint32_t a_base = smem_u32(smem + DenseSmem::a), b_base = smem_u32(smem + DenseSmem::b);
+      uint32_t it = 0, k = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++k) {
+        mbar_wait(tmem_empty, (k & 1) ^ 1);
+        tc_fence_after_sync();
+        for (int kb = 0; kb < kDKBlocks; ++kb, ++it) {
+          const uint32_t s = it % kDStages, ph = (it / kDStages) & 1;
+          mbar_wait(&full[s], ph);
+          tc_fence_after_sync();
+#pragma unroll
+          for (int ks = 0; ks < kDK / 16; ++ks) {
+            const uint64_t bd = make_smem_desc(b_base + s * kDTileBytes + ks * 32, 16, 1024, 2);
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+              const uint64_t ad = make_smem_desc(a_base + s * kDTileBytes + m * 16384 + ks * 32, 16, 1024, 2);
+              mma_bf16_ss(tmem + m * 256, ad, bd, idesc, (kb | ks) != 0);
+            }
+          }
+          mma_commit(&empty[s]);
+        }
+        mma_commit(tmem_full);
+      }
+    }
+  } else {
+    const int q = warp & 3, m = (warp - 2) >> 2;
+    const float* b3s = reinterpret_cast<const float*>(smem + DenseSmem::b3);
+    uint32_t k = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++k) {
+      mbar_wait(tmem_full, k & 1);
+      tc_fence_after_sync();
+      const long long row = (long long)tile * kDM + m * 128 + q * 32 + lane;
+      float* dst = hbuf + row * 256;
+#pragma unroll 1
+      for (int cc = 0; cc < 16; cc += 2) {
+        uint32_t v0[16], v1[16];
+        tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + m * 256 + cc * 16, v0);
+        tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + m * 256 + cc * 16 + 16, v1);
+        tmem_ld_wait();
+        if (row < n) {
+#pragma unroll
+          for (int e = 0; e < 16; e += 4) {
+            const int c0 = cc * 16 + e;
+            float4 o;
+            o.x = fmaxf(__uint_as_float(v0[e]) + b3s[c0], 0.f);
+            o.y = fmaxf(__uint_as_float(v0[e + 1]) + b3s[c0 + 1], 0.f);
+            o.z = fmaxf(__uint_as_float(v0[e + 2]) + b3s[c0 + 2], 0.f);
+            o.w = fmaxf(__uint_as_float(v0[e + 3]) + b3s[c0 + 3], 0.f);
+            *reinterpret_cast<float4*>(dst + c0) = o;
+          }
+#pragma unroll
+          for (int e = 0; e < 16; e += 4) {
+            const int c0 = cc * 16 + 16 + e;
+            float4 o;
+            o.x = fmaxf(__uint_as_float(v1[e]) + b3s[c0], 0.f);
+            o.y = fmaxf(__uint_as_float(v1[e + 1]) + b3s[c0 + 1], 0.f);
+            o.z = fmaxf(__uint_as_float(v1[e + 2]) + b3s[c0 + 2], 0.f);
+            o.w = fmaxf(__uint_as_float(v1[e + 3]) + b3s[c0 + 3], 0.f);
+            *reinterpret_cast<float4*>(dst + c0) = o;
+          }
+        }
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty);
+    }
+  }
+
+  __syncwarp();
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+static uint16_t f2bf(float f) {   // round to nearest even, like cvt.rn.bf16.f32
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7FFFFFFFu) > 0x7F800000u) return (uint16_t)((u >> 16) | 0x40);
+  u += 0x7FFFu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+
+static PFN_cuTensorMapEncodeTiled get_encode() {
+  static PFN_cuTensorMapEncodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(p);
+  }
+  return fn;
+}
+
+// [rows][kVtFlat] bf16, K-major: box = 64 K elements (128 B) x 256 rows, 128B swizzle, OOB rows -> 0
+static int make_kmajor_map(CUtensorMap* m, const void* base, uint64_t rows) {
+  PFN_cuTensorMapEncodeTiled enc = get_encode();
+  MDC_REQUIRE(enc != nullptr, MDC_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  const cuuint64_t dims[2] = {(cuuint64_t)kVtFlat, rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)kVtFlat * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)kDK, (cuuint32_t)kDM};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MDC_REQUIRE(r == CUDA_SUCCESS, MDC_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return MDC_OK;
+}
+
+int pack_vt_bf16(mdc_handle_s* h) {
+  if (int e = pack_vt_small(h)) return e;
+  // conv1 image: 32 channel groups x {w0[8], w1[8], w2[8], bias[8]} fp32 (Keras (1,3,1,256) = [tap][ch])
+  {
+    std::vector<float> img(32 * 32);
+    const float* w1 = h->w[MDC_T_CONV1_K].data();
+    const float* b1 = h->w[MDC_T_CONV1_B].data();
+    for (int g = 0; g < 32; ++g)
+      for (int e = 0; e < 8; ++e) {
+        const int ch = g * 8 + e;
+        img[g * 32 + e] = w1[ch];
+        img[g * 32 + 8 + e] = w1[256 + ch];
+        img[g * 32 + 16 + e] = w1[512 + ch];
+        img[g * 32 + 24 + e] = b1[ch];
+      }
+    if (int e = h->vt_w1.reserve(img.size() * 4)) return e;
+    MDC_CUDA(cudaMemcpy(h->vt_w1.ptr, img.data(), img.size() * 4, cudaMemcpyHostToDevice));
+  }
+  // conv2 image: [chunk][tap][group][out 80][8 k] bf16, k = row*256 + ch (Keras (2,3,256,80) = [r][j][ch][o])
+  {
+    std::vector<uint16_t> img((size_t)kChunks * kBSlot / 2);
+    const float* w2 = h->w[MDC_T_CONV2_K].data();
+    for (int c = 0; c < kChunks; ++c)
+      for (int j = 0; j < 3; ++j)
+        for (int g = 0; g < kGroups; ++g)
+          for (int o = 0; o < 80; ++o)
+            for (int e = 0; e < 8; ++e) {
+              const int kk = c * kKC + g * 8 + e, r = kk >> 8, ch = kk & 255;
+              img[(size_t)c * (kBSlot / 2) + ((size_t)(j * kGroups + g) * 80 + o) * 8 + e] =
+                  f2bf(w2[((size_t)(r * 3 + j) * 256 + ch) * 80 + o]);
+            }
+    if (int e = h->vt_w2_bf16.reserve(img.size() * 2)) return e;
+    MDC_CUDA(cudaMemcpy(h->vt_w2_bf16.ptr, img.data(), img.size() * 2, cudaMemcpyHostToDevice));
+  }
+  // dense1 image: W3^T [256][10560] bf16 in this library's activation order (pos*80 + ch)
+  {
+    std::vector<float> w3p;
+    vt_permute_w3(h, w3p);
+    std::vector<uint16_t> img((size_t)kVtH * kVtFlat);
+    for (int kx = 0; kx < kVtFlat; ++kx)
+      for (int o = 0; o < kVtH; ++o) img[(size_t)o * kVtFlat + kx] = f2bf(w3p[(size_t)kx * kVtH + o]);
+    if (int e = h->vt_w3_bf16.reserve(img.size() * 2)) return e;
+    MDC_CUDA(cudaMemcpy(h->vt_w3_bf16.ptr, img.data(), img.size() * 2, cudaMemcpyHostToDevice));
+    if (!h->tmap_w3) h->tmap_w3 = aligned_alloc(64, sizeof(CUtensorMap));
+    if (int e = make_kmajor_map(reinterpret_cast<CUtensorMap*>(h->tmap_w3), h->vt_w3_bf16.ptr, kVtH)) return e;
+  }
+  MDC_CUDA(cudaFuncSetAttribute(vt_conv_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvSmem::total));
+  MDC_CUDA(cudaFuncSetAttribute(vt_dense_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DenseSmem::total));
+  return MDC_OK;
+}
+
+int launch_vt_bf16(mdc_handle_s* h, const float* x, int64_t n, float* probs, float* dense,
+                   int32_t* cls, unsigned long long* hist, cudaStream_t stream) {
+  constexpr int64_t CH = 65536;     // frames per pass: act = 1.38 GB, h = 64 MB of workspace
+  const int64_t cap = n < CH ? n : CH;
+  if (n == 0) return MDC_OK;
+  if (int e = h->ws_act.reserve((size_t)cap * kVtFlat * 2)) return e;
+  if (int e = h->ws_h.reserve((size_t)cap * kVtH * 4)) return e;
+  __nv_bfloat16* act = reinterpret_cast<__nv_bfloat16*>(h->ws_act.ptr);
+  float* hb = reinterpret_cast<float*>(h->ws_h.ptr);
+  for (int64_t s = 0; s < n; s += CH) {
+    const int64_t m = (n - s) < CH ? (n - s) : CH;
+    const long long num_st = (m * 132 + kOutRows - 1) / kOutRows;
+    const unsigned grid_c = (unsigned)(num_st < h->num_sms ? num_st : h->num_sms);
+    prof_begin(h, stream);
+    vt_conv_bf16_kernel<<<grid_c, kConvThreads, ConvSmem::total, stream>>>(
+        x + s * 256, m, reinterpret_cast<const uint8_t*>(h->vt_w1.ptr), reinterpret_cast<const float*>(h->vt_b2.ptr),
+        reinterpret_cast<const uint8_t*>(h->vt_w2_bf16.ptr), act, num_st);
+    prof_end(h, stream);
+    MDC_CUDA(cudaGetLastError());
+    CUtensorMap map_a;
+    if (int e = make_kmajor_map(&map_a, act, (uint64_t)m)) return e;
+    const int tiles = (int)((m + kDM - 1) / kDM);
+    const unsigned grid_d = (unsigned)(tiles < h->num_sms ? tiles : h->num_sms);
+    vt_dense_bf16_kernel<<<grid_d, kDenseThreads, DenseSmem::total, stream>>>(
+        map_a, *reinterpret_cast<const CUtensorMap*>(h->tmap_w3), reinterpret_cast<const float*>(h->vt_b3.ptr), hb, m,
+        tiles);
+    h->launches += 2;
+    MDC_CUDA(cudaGetLastError());
+    if (int e = launch_vt_head(h, hb, m, probs ? probs + s * h->C : nullptr, dense ? dense + s * h->C : nullptr,
+                               cls ? cls + s : nullptr, hist, stream))
+      return e;
+  }
+  return MDC_OK;
+}
+
+}  // namespace mdc
