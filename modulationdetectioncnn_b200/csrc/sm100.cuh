@@ -12,6 +12,21 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// ---------------------------------------------------------------- warp-uniform helpers
+// warp index the compiler can prove uniform (so role branches and loop counters live in uniform
+// registers and tcgen05/TMA instructions are issued without a per-lane waterfall loop)
+__device__ __forceinline__ int uniform_warp_idx() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+// true in exactly one lane of a converged warp
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "elect.sync _|P1, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P1;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -138,6 +153,16 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
   d |= (uint64_t)(swizzle_code & 7) << 61;
   return d;
 }
+// The same descriptor split into a constant high word and a low word whose address field can be
+// advanced with a plain 32-bit add of (byte offset >> 4) (no carry: shared addresses < 256 KB).
+__device__ __forceinline__ uint32_t smem_desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+  return ((saddr >> 4) & 0x3FFF) | (((lbo_bytes >> 4) & 0x3FFF) << 16);
+}
+__host__ __device__ constexpr uint32_t smem_desc_hi(uint32_t sbo_bytes, uint32_t swizzle_code) {
+  return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14) | ((swizzle_code & 7) << 29);
+}
+__device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
+
 // Instruction descriptor for kind::f16 with bf16 A/B (both K-major), fp32 accumulate:
 //   [4,6) D fmt = 1 (f32)  [7,10) A fmt = 1 (bf16)  [10,13) B fmt = 1 (bf16)
 //   [15] A major = 0 (K)   [16] B major = 0 (K)     [17,23) N >> 3   [24,29) M >> 4

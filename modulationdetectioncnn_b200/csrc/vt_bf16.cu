@@ -96,7 +96,7 @@ vt_conv_bf16_kernel(const float* __restrict__ x, long long n, const uint8_t* __r
   uint64_t* tmem_empty = tmem_full + kNT;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + ConvSmem::tmem_slot);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
   const long long total_rows = n * 132;
 
   // ---- one-time setup
@@ -123,55 +123,63 @@ vt_conv_bf16_kernel(const float* __restrict__ x, long long n, const uint8_t* __r
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 0) {
-    // ================= TMA: frames of the super-tile + the W2 chunk stream
-    if (lane == 0) {
-      uint32_t it = 0, k = 0;
-      for (long long st = blockIdx.x; st < num_st; st += gridDim.x, ++k) {
-        const long long f0 = (st * kOutRows) / 132;
-        const long long left = n - f0;
-        const uint32_t nf = left < kXFrames ? (uint32_t)left : (uint32_t)kXFrames;
-        mbar_wait(x_empty, (k & 1) ^ 1);
+    // ================= TMA: frames of the super-tile + the W2 chunk stream (whole warp loops,
+    // one elected lane issues, so every operand stays in uniform registers)
+    uint32_t it = 0, k = 0;
+    for (long long st = blockIdx.x; st < num_st; st += gridDim.x, ++k) {
+      const long long f0 = (st * kOutRows) / 132;
+      const long long left = n - f0;
+      const uint32_t nf = left < kXFrames ? (uint32_t)left : (uint32_t)kXFrames;
+      mbar_wait(x_empty, (k & 1) ^ 1);
+      if (elect_one()) {
         mbar_arrive_expect_tx(x_full, nf * 1024);
         bulk_g2s(smem + ConvSmem::xs, x + f0 * 256, nf * 1024, x_full);
-        for (int c = 0; c < kChunks; ++c, ++it) {
-          const uint32_t s = it % kStages, ph = (it / kStages) & 1;
-          mbar_wait(&empty[s], ph ^ 1);
+      }
+      __syncwarp();
+      for (int c = 0; c < kChunks; ++c, ++it) {
+        const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        if (elect_one()) {
           mbar_arrive_expect_tx(&full[s], kBSlot);
           bulk_g2s(smem + ConvSmem::b + s * kBSlot, w2img + (size_t)c * kBSlot, kBSlot, &full[s]);
         }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer (one thread)
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(128, 80);
-      const uint32_t a_base = smem_u32(smem + ConvSmem::a), b_base = smem_u32(smem + ConvSmem::b);
-      uint32_t it = 0, k = 0;
-      for (long long st = blockIdx.x; st < num_st; st += gridDim.x, ++k) {
-        for (int c = 0; c < kChunks; ++c, ++it) {
-          const uint32_t s = it % kStages, ph = (it / kStages) & 1;
-          mbar_wait(&full[s], ph);
-          tc_fence_after_sync();
-          const uint32_t a_slot = a_base + s * kASlot, b_slot = b_base + s * kBSlot;
+    // ================= MMA issuer: whole warp loops, one elected lane issues
+    const uint32_t idesc = make_idesc_bf16(128, 80);
+    const uint32_t a_base = smem_u32(smem + ConvSmem::a), b_base = smem_u32(smem + ConvSmem::b);
+    constexpr uint32_t hi = smem_desc_hi(128, 0);
+    uint32_t it = 0, k = 0;
+    for (long long st = blockIdx.x; st < num_st; st += gridDim.x, ++k) {
+      for (int c = 0; c < kChunks; ++c, ++it) {
+        const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+        mbar_wait(&full[s], ph);
+        if (c == 0) {
+#pragma unroll
+          for (int t = 0; t < kNT; ++t) mbar_wait(&tmem_empty[t], (k & 1) ^ 1);
+        }
+        tc_fence_after_sync();
+        if (elect_one()) {
+          const uint32_t a_lo = smem_desc_lo(a_base + s * kASlot, kALbo);
+          const uint32_t b_lo = smem_desc_lo(b_base + s * kBSlot, kBLbo);
 #pragma unroll
           for (int t = 0; t < kNT; ++t) {
-            if (c == 0) {
-              mbar_wait(&tmem_empty[t], (k & 1) ^ 1);
-              tc_fence_after_sync();
-            }
 #pragma unroll
             for (int g2 = 0; g2 < kKC / 16; ++g2) {
 #pragma unroll
               for (int j = 0; j < 3; ++j) {
-                const uint64_t ad = make_smem_desc(a_slot + (2 * g2) * kALbo + (128 * t + j) * 16, kALbo, 128, 0);
-                const uint64_t bd = make_smem_desc(b_slot + (j * kGroups + 2 * g2) * kBLbo, kBLbo, 128, 0);
-                mma_bf16_ss(tmem + t * 80, ad, bd, idesc, (c | g2 | j) != 0);
+                const uint32_t ao = ((2 * g2) * kALbo + (128 * t + j) * 16) >> 4;
+                const uint32_t bo = ((j * kGroups + 2 * g2) * kBLbo) >> 4;
+                mma_bf16_ss(tmem + t * 80, desc64(a_lo + ao, hi), desc64(b_lo + bo, hi), idesc, (c | g2 | j) != 0);
               }
             }
             if (c == kChunks - 1) mma_commit(&tmem_full[t]);
           }
           mma_commit(&empty[s]);
         }
+        __syncwarp();
       }
     }
   } else if (warp < kProdWarp0) {
@@ -328,7 +336,7 @@ vt_dense_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   uint64_t* tmem_full = bars + 2 * kDStages;
   uint64_t* tmem_empty = tmem_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + DenseSmem::tmem_slot);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
 
   for (int i = tid; i < 256; i += kDenseThreads) reinterpret_cast<float*>(smem + DenseSmem::b3)[i] = b3g[i];
   if (tid == 0) {
@@ -349,42 +357,44 @@ vt_dense_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        for (int kb = 0; kb < kDKBlocks; ++kb, ++it) {
-          const uint32_t s = it % kDStages, ph = (it / kDStages) & 1;
-          mbar_wait(&empty[s], ph ^ 1);
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int kb = 0; kb < kDKBlocks; ++kb, ++it) {
+        const uint32_t s = it % kDStages, ph = (it / kDStages) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        if (elect_one()) {
           mbar_arrive_expect_tx(&full[s], 2 * kDTileBytes);
           tma_load_2d(smem + DenseSmem::a + s * kDTileBytes, &map_a, kb * kDK, tile * kDM, &full[s]);
           tma_load_2d(smem + DenseSmem::b + s * kDTileBytes, &map_b, kb * kDK, 0, &full[s]);
         }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(128, 256);
-      const uint32_t a_base = smem_u32(smem + DenseSmem::a), b_base = smem_u32(smem + DenseSmem::b);
-      uint32_t it = 0, k = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++k) {
-        mbar_wait(tmem_empty, (k & 1) ^ 1);
+    const uint32_t idesc = make_idesc_bf16(128, 256);
+    const uint32_t a_base = smem_u32(smem + DenseSmem::a), b_base = smem_u32(smem + DenseSmem::b);
+    constexpr uint32_t hi = smem_desc_hi(1024, 2);
+    uint32_t it = 0, k = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++k) {
+      mbar_wait(tmem_empty, (k & 1) ^ 1);
+      for (int kb = 0; kb < kDKBlocks; ++kb, ++it) {
+        const uint32_t s = it % kDStages, ph = (it / kDStages) & 1;
+        mbar_wait(&full[s], ph);
         tc_fence_after_sync();
-        for (int kb = 0; kb < kDKBlocks; ++kb, ++it) {
-          const uint32_t s = it % kDStages, ph = (it / kDStages) & 1;
-          mbar_wait(&full[s], ph);
-          tc_fence_after_sync();
+        if (elect_one()) {
+          const uint32_t a_lo = smem_desc_lo(a_base + s * kDTileBytes, 16);
+          const uint32_t b_lo = smem_desc_lo(b_base + s * kDTileBytes, 16);
 #pragma unroll
           for (int ks = 0; ks < kDK / 16; ++ks) {
-            const uint64_t bd = make_smem_desc(b_base + s * kDTileBytes + ks * 32, 16, 1024, 2);
 #pragma unroll
-            for (int m = 0; m < 2; ++m) {
-              const uint64_t ad = make_smem_desc(a_base + s * kDTileBytes + m * 16384 + ks * 32, 16, 1024, 2);
-              mma_bf16_ss(tmem + m * 256, ad, bd, idesc, (kb | ks) != 0);
-            }
+            for (int m = 0; m < 2; ++m)
+              mma_bf16_ss(tmem + m * 256, desc64(a_lo + ((m * 16384 + ks * 32) >> 4), hi),
+                          desc64(b_lo + ((ks * 32) >> 4), hi), idesc, (kb | ks) != 0);
           }
           mma_commit(&empty[s]);
+          if (kb == kDKBlocks - 1) mma_commit(tmem_full);
         }
-        mma_commit(tmem_full);
+        __syncwarp();
       }
     }
   } else {
