@@ -34,22 +34,24 @@ void vt_permute_w3(const mdc_handle_s* h, std::vector<float>& out);
 
 // ------------------------------------------------------------------------------------------
 // conv kernel geometry
-constexpr int kNT = 6;                    // accumulator tiles (128 rows x 80 cols) per super-tile
-constexpr int kTapeRows = 128 * kNT;      // 768 tape rows staged per super-tile
-constexpr int kOutRows = kTapeRows - 2;   // 766 conv2 rows produced per super-tile (2-row halo)
-constexpr int kKC = 16;                   // K channels per pipeline chunk (one UMMA K step)
-constexpr int kGroups = kKC / 8;          // 8-channel groups per chunk
-constexpr int kChunks = 512 / kKC;        // chunks per super-tile (K = 2 rows x 256 channels)
-constexpr int kStages = 5;
-constexpr int kALbo = kTapeRows * 16;     // bytes between 8-channel groups of the A image
+constexpr int kNT = 3;                    // accumulator tiles (128 rows x 80 cols) per super-tile
+constexpr int kTapeRows = 128 * kNT;      // 384 tape rows staged per super-tile
+constexpr int kOutRows = kTapeRows - 2;   // 382 conv2 rows produced per super-tile (2-row halo)
+constexpr int kCC = 16;                   // conv1 channels per pipeline chunk ...
+constexpr int kKC = 2 * kCC;              // ... x 2 input rows (I, Q) = 32 K values = two UMMA K steps
+constexpr int kGroups = kKC / 8;          // 8-value K groups per chunk: g = 2 * (channel half) + row
+constexpr int kChunks = 256 / kCC;        // 16 chunks per super-tile
+constexpr int kStages = 4;
+constexpr int kALbo = kTapeRows * 16;     // bytes between K groups of the A image
 constexpr int kASlot = kGroups * kALbo;   // 24,576
-constexpr int kBLbo = 80 * 16;            // bytes between 8-channel groups of the B image
-constexpr int kBSlot = 3 * kGroups * kBLbo;   // 7,680: [tap][group][80][8]
-constexpr int kXFrames = 7;               // frames a super-tile's tape rows can touch
+constexpr int kBLbo = 80 * 16;            // bytes between K groups of the B image
+constexpr int kBSlot = 3 * kGroups * kBLbo;   // 15,360: [tap][group][80][8]
+constexpr int kXFrames = 4;               // frames a super-tile's tape rows can touch
 constexpr int kOutTile = 128 * 160;       // one 128 x 80 bf16 output tile
-constexpr int kConvThreads = 14 * 32;     // TMA, MMA, 4 epilogue, 8 producer warps
 constexpr int kProdWarp0 = 6;
-constexpr int kProdWarps = 8;
+constexpr int kProdWarps = kTapeRows / 32;             // 12: one tape row per producer thread
+constexpr int kConvThreads = (kProdWarp0 + kProdWarps) * 32;   // TMA, MMA, 4 epilogue, 12 producers
+constexpr int kAccCols = kNT * 80;        // TMEM columns per accumulator buffer (two buffers)
 
 struct ConvSmem {
   static constexpr int a = 0;
@@ -59,12 +61,13 @@ struct ConvSmem {
   static constexpr int w1 = out + 2 * kOutTile;       // 32 groups x 128 B
   static constexpr int b2 = w1 + 32 * 128;            // 80 floats
   static constexpr int bars = b2 + 320;
-  // full[S], empty[S], x_full, x_empty, tmem_full[NT], tmem_empty[NT]
-  static constexpr int nbars = 2 * kStages + 2 + 2 * kNT;
+  // full[S], empty[S], x_full, x_empty, tmem_full[2], tmem_empty[2]
+  static constexpr int nbars = 2 * kStages + 2 + 4;
   static constexpr int tmem_slot = bars + nbars * 8;
   static constexpr int total = tmem_slot + 16;
 };
 static_assert(ConvSmem::total <= 232448, "conv kernel shared memory exceeds 227 KB");
+static_assert(2 * kAccCols <= 512, "accumulators exceed TMEM");
 
 __device__ __forceinline__ uint64_t pack_dup(float v) {
   uint64_t d;
@@ -82,18 +85,32 @@ __device__ __forceinline__ uint32_t relu_pack(uint64_t v) {   // {lo, hi} fp32 -
   return cvt_relu_bf16x2(hi, lo);
 }
 
+// 8 conv1 channels of one tape row: relu(x0 w0 + x1 w1 + x2 w2 + b) -> 8 x bf16 (16 B)
+__device__ __forceinline__ uint4 conv1_item(uint64_t x0, uint64_t x1, uint64_t x2, const ulonglong2 (&w)[8],
+                                            uint32_t m) {
+  uint64_t a0 = fma2_u(x0, w[0].x, w[6].x), a1 = fma2_u(x0, w[0].y, w[6].y);
+  uint64_t a2 = fma2_u(x0, w[1].x, w[7].x), a3 = fma2_u(x0, w[1].y, w[7].y);
+  a0 = fma2_u(x1, w[2].x, a0); a1 = fma2_u(x1, w[2].y, a1);
+  a2 = fma2_u(x1, w[3].x, a2); a3 = fma2_u(x1, w[3].y, a3);
+  a0 = fma2_u(x2, w[4].x, a0); a1 = fma2_u(x2, w[4].y, a1);
+  a2 = fma2_u(x2, w[5].x, a2); a3 = fma2_u(x2, w[5].y, a3);
+  return make_uint4(relu_pack(a0) & m, relu_pack(a1) & m, relu_pack(a2) & m, relu_pack(a3) & m);
+}
+
 __global__ void __launch_bounds__(kConvThreads, 1)
 vt_conv_bf16_kernel(const float* __restrict__ x, long long n, const uint8_t* __restrict__ w1img,
                     const float* __restrict__ b2g, const uint8_t* __restrict__ w2img,
-                    __nv_bfloat16* __restrict__ act, long long num_st) {
+                    __nv_bfloat16* __restrict__ act, long long num_st, int dbg) {
+  // dbg (timing experiments only, results are garbage): 1 = producers skip conv1 math and stores,
+  // 2 = MMA warp skips the MMAs, 4 = epilogue skips TMEM loads / math / stores
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ConvSmem::bars);
   uint64_t* full = bars;
   uint64_t* empty = bars + kStages;
   uint64_t* x_full = bars + 2 * kStages;
   uint64_t* x_empty = x_full + 1;
-  uint64_t* tmem_full = x_empty + 1;
-  uint64_t* tmem_empty = tmem_full + kNT;
+  uint64_t* tmem_full = x_empty + 1;     // [2] accumulator buffers
+  uint64_t* tmem_empty = tmem_full + 2;  // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + ConvSmem::tmem_slot);
 
   const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
@@ -110,9 +127,9 @@ vt_conv_bf16_kernel(const float* __restrict__ x, long long n, const uint8_t* __r
     }
     mbar_init(x_full, 1);
     mbar_init(x_empty, kProdWarps);
-    for (int t = 0; t < kNT; ++t) {
-      mbar_init(&tmem_full[t], 1);
-      mbar_init(&tmem_empty[t], 4);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full[b], 1);
+      mbar_init(&tmem_empty[b], 4);
     }
     fence_barrier_init();
   }
@@ -153,31 +170,31 @@ vt_conv_bf16_kernel(const float* __restrict__ x, long long n, const uint8_t* __r
     constexpr uint32_t hi = smem_desc_hi(128, 0);
     uint32_t it = 0, k = 0;
     for (long long st = blockIdx.x; st < num_st; st += gridDim.x, ++k) {
+      const uint32_t buf = k & 1;
+      const uint32_t acc = tmem + buf * kAccCols;
+      mbar_wait(&tmem_empty[buf], ((k >> 1) & 1) ^ 1);     // epilogue drained this buffer
       for (int c = 0; c < kChunks; ++c, ++it) {
         const uint32_t s = it % kStages, ph = (it / kStages) & 1;
         mbar_wait(&full[s], ph);
-        if (c == 0) {
-#pragma unroll
-          for (int t = 0; t < kNT; ++t) mbar_wait(&tmem_empty[t], (k & 1) ^ 1);
-        }
         tc_fence_after_sync();
         if (elect_one()) {
           const uint32_t a_lo = smem_desc_lo(a_base + s * kASlot, kALbo);
           const uint32_t b_lo = smem_desc_lo(b_base + s * kBSlot, kBLbo);
 #pragma unroll
           for (int t = 0; t < kNT; ++t) {
+            if (dbg & 2) continue;
 #pragma unroll
-            for (int g2 = 0; g2 < kKC / 16; ++g2) {
+            for (int ks = 0; ks < kKC / 16; ++ks) {
 #pragma unroll
               for (int j = 0; j < 3; ++j) {
-                const uint32_t ao = ((2 * g2) * kALbo + (128 * t + j) * 16) >> 4;
-                const uint32_t bo = ((j * kGroups + 2 * g2) * kBLbo) >> 4;
-                mma_bf16_ss(tmem + t * 80, desc64(a_lo + ao, hi), desc64(b_lo + bo, hi), idesc, (c | g2 | j) != 0);
+                const uint32_t ao = ((2 * ks) * kALbo + (128 * t + j) * 16) >> 4;
+                const uint32_t bo = ((j * kGroups + 2 * ks) * kBLbo) >> 4;
+                mma_bf16_ss(acc + t * 80, desc64(a_lo + ao, hi), desc64(b_lo + bo, hi), idesc, (c | ks | j) != 0);
               }
             }
-            if (c == kChunks - 1) mma_commit(&tmem_full[t]);
           }
           mma_commit(&empty[s]);
+          if (c == kChunks - 1) mma_commit(&tmem_full[buf]);
         }
         __syncwarp();
       }
@@ -186,37 +203,47 @@ vt_conv_bf16_kernel(const float* __restrict__ x, long long n, const uint8_t* __r
     // ================= epilogue: TMEM -> +bias, ReLU, bf16 -> smem tile -> bulk store
     const int q = warp & 3;                      // TMEM lane quarter this warp may read
     const bool leader = (warp == 2 && lane == 0);
-    const float* b2s = reinterpret_cast<const float*>(smem + ConvSmem::b2);
+    const float4* b2s = reinterpret_cast<const float4*>(smem + ConvSmem::b2);
     uint32_t k = 0, tile_ctr = 0;
     for (long long st = blockIdx.x; st < num_st; st += gridDim.x, ++k) {
       const long long r0 = st * kOutRows;
+      const uint32_t buf = k & 1;
+      mbar_wait(&tmem_full[buf], (k >> 1) & 1);
+      tc_fence_after_sync();
 #pragma unroll 1
       for (int t = 0; t < kNT; ++t, ++tile_ctr) {
         uint8_t* obuf = smem + ConvSmem::out + (tile_ctr & 1) * kOutTile;
         if (leader) bulk_wait_read<1>();          // the store issued two tiles ago has drained obuf
         named_bar_sync(1, 128);
-        mbar_wait(&tmem_full[t], k & 1);
-        tc_fence_after_sync();
         uint32_t v[80];
+        if (!(dbg & 4)) {
 #pragma unroll
-        for (int cc = 0; cc < 5; ++cc) {
-          uint32_t(&vv)[16] = *reinterpret_cast<uint32_t(*)[16]>(&v[cc * 16]);
-          tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + t * 80 + cc * 16, vv);
+          for (int cc = 0; cc < 5; ++cc) {
+            uint32_t(&vv)[16] = *reinterpret_cast<uint32_t(*)[16]>(&v[cc * 16]);
+            tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + buf * kAccCols + t * 80 + cc * 16, vv);
+          }
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int i = 0; i < 80; ++i) v[i] = 0;
         }
-        tmem_ld_wait();
-        tc_fence_before_sync();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty[t]);
+        if (t == kNT - 1) {                       // whole buffer read: hand it back to the MMA warp
+          tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+        }
         uint8_t* orow = obuf + (q * 32 + lane) * 160;
 #pragma unroll
         for (int c8 = 0; c8 < 10; ++c8) {
-          uint32_t p[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int col = c8 * 8 + 2 * e;
-            p[e] = cvt_relu_bf16x2(__uint_as_float(v[col + 1]) + b2s[col + 1], __uint_as_float(v[col]) + b2s[col]);
-          }
-          *reinterpret_cast<uint4*>(orow + c8 * 16) = make_uint4(p[0], p[1], p[2], p[3]);
+          if (dbg & 4) break;
+          const float4 ba = b2s[2 * c8], bb = b2s[2 * c8 + 1];
+          const uint32_t* vv = &v[c8 * 8];
+          const uint4 o = make_uint4(
+              cvt_relu_bf16x2(__uint_as_float(vv[1]) + ba.y, __uint_as_float(vv[0]) + ba.x),
+              cvt_relu_bf16x2(__uint_as_float(vv[3]) + ba.w, __uint_as_float(vv[2]) + ba.z),
+              cvt_relu_bf16x2(__uint_as_float(vv[5]) + bb.y, __uint_as_float(vv[4]) + bb.x),
+              cvt_relu_bf16x2(__uint_as_float(vv[7]) + bb.w, __uint_as_float(vv[6]) + bb.z));
+          *reinterpret_cast<uint4*>(orow + c8 * 16) = o;
         }
         fence_proxy_async_smem();
         named_bar_sync(2, 128);
@@ -225,32 +252,32 @@ vt_conv_bf16_kernel(const float* __restrict__ x, long long n, const uint8_t* __r
           long long rows = kOutRows - 128 * t;
           if (rows > 128) rows = 128;
           if (row_lo + rows > total_rows) rows = total_rows - row_lo;
-          if (rows > 0) bulk_s2g(act + row_lo * 80, obuf, (uint32_t)rows * 160);
+          if (rows > 0 && !(dbg & 4)) bulk_s2g(act + row_lo * 80, obuf, (uint32_t)rows * 160);
           bulk_commit();
         }
       }
     }
     if (leader) bulk_wait<0>();
   } else {
-    // ================= conv1 producers: fp32 FMA -> ReLU -> bf16 -> A operand image
+    // ================= conv1 producers: fp32 FMA -> ReLU -> bf16 -> A operand image.
+    // One tape row per thread; a chunk is 16 channels x {I row, Q row}, so each 8-channel weight
+    // set loaded from shared memory is used for both input rows.
     const int pw = warp - kProdWarp0;
+    const int row = pw * 32 + lane;
     const float* xs = reinterpret_cast<const float*>(smem + ConvSmem::xs);
     const ulonglong2* w1s = reinterpret_cast<const ulonglong2*>(smem + ConvSmem::w1);
     uint32_t it = 0, k = 0;
     for (long long st = blockIdx.x; st < num_st; st += gridDim.x, ++k) {
       const long long t0 = st * kOutRows;          // first tape row of this super-tile
       const long long f0 = t0 / 132;
+      const long long tp = t0 + row;
+      const long long f = tp / 132;
+      const int p = (int)(tp - f * 132);
+      const bool valid = (p >= 2) && (f < n);
+      const uint32_t m = valid ? 0xFFFFFFFFu : 0u;
       mbar_wait(x_full, k & 1);
-      // this thread owns tape rows (pw + 8 i) * 32 + lane, i = 0..2, for the whole super-tile
-      uint64_t xd[3][2][3];
-      uint32_t mask[3];
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        const long long tp = t0 + (pw + kProdWarps * i) * 32 + lane;
-        const long long f = tp / 132;
-        const int p = (int)(tp - f * 132);
-        const bool valid = (p >= 2) && (f < n);
-        mask[i] = valid ? 0xFFFFFFFFu : 0u;
+      uint64_t xd[2][3];
+      {
         const float* xf = xs + (f - f0) * 256;
 #pragma unroll
         for (int r = 0; r < 2; ++r)
@@ -258,41 +285,34 @@ vt_conv_bf16_kernel(const float* __restrict__ x, long long n, const uint8_t* __r
           for (int j = 0; j < 3; ++j) {
             const int xi = p - 4 + j;               // conv1 position p-2 reads x[p-4 .. p-2]
             const float xv = (valid && xi >= 0 && xi < 128) ? xf[r * 128 + xi] : 0.f;
-            xd[i][r][j] = pack_dup(xv);
+            xd[r][j] = pack_dup(xv);
           }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(x_empty);
-#pragma unroll
-      for (int r = 0; r < 2; ++r) {
 #pragma unroll 1
-        for (int cr = 0; cr < kChunks / 2; ++cr, ++it) {
-          const uint32_t s = it % kStages, ph = (it / kStages) & 1;
-          mbar_wait(&empty[s], ph ^ 1);
-          uint8_t* aslot = smem + ConvSmem::a + s * kASlot;
+      for (int c = 0; c < kChunks; ++c, ++it) {
+        // compute the chunk into registers first: nothing here depends on the stage being free
+        uint4 o[kGroups];
 #pragma unroll
-          for (int g = 0; g < kGroups; ++g) {
-            const ulonglong2* wg = w1s + (cr * kGroups + g) * 8;
-            const ulonglong2 wa0 = wg[0], wa1 = wg[1], wb0 = wg[2], wb1 = wg[3], wc0 = wg[4], wc1 = wg[5],
-                             bb0 = wg[6], bb1 = wg[7];
+        for (int hc = 0; hc < kCC / 8; ++hc) {
+          if (dbg & 1) break;
+          ulonglong2 w[8];
 #pragma unroll
-            for (int i = 0; i < 3; ++i) {
-              const uint64_t x0 = xd[i][r][0], x1 = xd[i][r][1], x2 = xd[i][r][2];
-              uint64_t a0 = fma2_u(x0, wa0.x, bb0.x), a1 = fma2_u(x0, wa0.y, bb0.y);
-              uint64_t a2 = fma2_u(x0, wa1.x, bb1.x), a3 = fma2_u(x0, wa1.y, bb1.y);
-              a0 = fma2_u(x1, wb0.x, a0); a1 = fma2_u(x1, wb0.y, a1);
-              a2 = fma2_u(x1, wb1.x, a2); a3 = fma2_u(x1, wb1.y, a3);
-              a0 = fma2_u(x2, wc0.x, a0); a1 = fma2_u(x2, wc0.y, a1);
-              a2 = fma2_u(x2, wc1.x, a2); a3 = fma2_u(x2, wc1.y, a3);
-              const uint32_t m = mask[i];
-              const uint4 o = make_uint4(relu_pack(a0) & m, relu_pack(a1) & m, relu_pack(a2) & m, relu_pack(a3) & m);
-              *reinterpret_cast<uint4*>(aslot + g * kALbo + ((pw + kProdWarps * i) * 32 + lane) * 16) = o;
-            }
-          }
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&full[s]);
+          for (int i = 0; i < 8; ++i) w[i] = w1s[(c * (kCC / 8) + hc) * 8 + i];
+          o[2 * hc] = conv1_item(xd[0][0], xd[0][1], xd[0][2], w, m);
+          o[2 * hc + 1] = conv1_item(xd[1][0], xd[1][1], xd[1][2], w, m);
         }
+        const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        uint8_t* arow = smem + ConvSmem::a + s * kASlot + row * 16;
+        if (!(dbg & 1)) {
+#pragma unroll
+          for (int g = 0; g < kGroups; ++g) *reinterpret_cast<uint4*>(arow + g * kALbo) = o[g];
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full[s]);
       }
     }
   }
@@ -502,7 +522,8 @@ int pack_vt_bf16(mdc_handle_s* h) {
     if (int e = h->vt_w1.reserve(img.size() * 4)) return e;
     MDC_CUDA(cudaMemcpy(h->vt_w1.ptr, img.data(), img.size() * 4, cudaMemcpyHostToDevice));
   }
-  // conv2 image: [chunk][tap][group][out 80][8 k] bf16, k = row*256 + ch (Keras (2,3,256,80) = [r][j][ch][o])
+  // conv2 image: [chunk][tap][group][out 80][8 k] bf16; chunk c = conv1 channels 16c..16c+15,
+  // group g = 2*(channel half) + input row  (Keras (2,3,256,80) = [r][j][ch][o])
   {
     std::vector<uint16_t> img((size_t)kChunks * kBSlot / 2);
     const float* w2 = h->w[MDC_T_CONV2_K].data();
@@ -511,7 +532,7 @@ int pack_vt_bf16(mdc_handle_s* h) {
         for (int g = 0; g < kGroups; ++g)
           for (int o = 0; o < 80; ++o)
             for (int e = 0; e < 8; ++e) {
-              const int kk = c * kKC + g * 8 + e, r = kk >> 8, ch = kk & 255;
+              const int r = g & 1, ch = c * kCC + (g >> 1) * 8 + e;
               img[(size_t)c * (kBSlot / 2) + ((size_t)(j * kGroups + g) * 80 + o) * 8 + e] =
                   f2bf(w2[((size_t)(r * 3 + j) * 256 + ch) * 80 + o]);
             }
@@ -544,6 +565,7 @@ int launch_vt_bf16(mdc_handle_s* h, const float* x, int64_t n, float* probs, flo
   if (int e = h->ws_h.reserve((size_t)cap * kVtH * 4)) return e;
   __nv_bfloat16* act = reinterpret_cast<__nv_bfloat16*>(h->ws_act.ptr);
   float* hb = reinterpret_cast<float*>(h->ws_h.ptr);
+  static const int dbg = getenv("MDC_VT_DEBUG") ? atoi(getenv("MDC_VT_DEBUG")) : 0;   // timing experiments
   for (int64_t s = 0; s < n; s += CH) {
     const int64_t m = (n - s) < CH ? (n - s) : CH;
     const long long num_st = (m * 132 + kOutRows - 1) / kOutRows;
@@ -551,7 +573,7 @@ int launch_vt_bf16(mdc_handle_s* h, const float* x, int64_t n, float* probs, flo
     prof_begin(h, stream);
     vt_conv_bf16_kernel<<<grid_c, kConvThreads, ConvSmem::total, stream>>>(
         x + s * 256, m, reinterpret_cast<const uint8_t*>(h->vt_w1.ptr), reinterpret_cast<const float*>(h->vt_b2.ptr),
-        reinterpret_cast<const uint8_t*>(h->vt_w2_bf16.ptr), act, num_st);
+        reinterpret_cast<const uint8_t*>(h->vt_w2_bf16.ptr), act, num_st, dbg);
     prof_end(h, stream);
     MDC_CUDA(cudaGetLastError());
     CUtensorMap map_a;
