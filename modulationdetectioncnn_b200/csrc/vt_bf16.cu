@@ -33,7 +33,11 @@ int pack_vt_small(mdc_handle_s* h);
 void vt_permute_w3(const mdc_handle_s* h, std::vector<float>& out);
 
 // ------------------------------------------------------------------------------------------
-// conv kernel geometry
+// conv kernel geometry.  CTAs work in pairs (cluster of 2, tcgen05 cta_group::2): each CTA owns
+// its own super-tile (tape rows, conv1 producers, accumulators, epilogue) and HALF of every W2
+// chunk; one M = 256 MMA issued by the pair's leader covers a 128-row tile of each CTA, so the
+// B operand is fetched from shared memory once per pair (measured: 45 cycles per MMA against 52
+// for the single-CTA M = 128 x N = 80 shape, tools/umma_rate.cu / tools/umma2_probe.cu).
 constexpr int kNT = 3;                    // accumulator tiles (128 rows x 80 cols) per super-tile
 constexpr int kTapeRows = 128 * kNT;      // 384 tape rows staged per super-tile
 constexpr int kOutRows = kTapeRows - 2;   // 382 conv2 rows produced per super-tile (2-row halo)
@@ -41,11 +45,12 @@ constexpr int kCC = 16;                   // conv1 channels per pipeline chunk .
 constexpr int kKC = 2 * kCC;              // ... x 2 input rows (I, Q) = 32 K values = two UMMA K steps
 constexpr int kGroups = kKC / 8;          // 8-value K groups per chunk: g = 2 * (channel half) + row
 constexpr int kChunks = 256 / kCC;        // 16 chunks per super-tile
-constexpr int kStages = 4;
+constexpr int kStages = 5;
 constexpr int kALbo = kTapeRows * 16;     // bytes between K groups of the A image
 constexpr int kASlot = kGroups * kALbo;   // 24,576
-constexpr int kBLbo = 80 * 16;            // bytes between K groups of the B image
-constexpr int kBSlot = 3 * kGroups * kBLbo;   // 15,360: [tap][group][80][8]
+constexpr int kBHalf = 40;                // W2 output channels held by each CTA of the pair
+constexpr int kBLbo = kBHalf * 16;        // bytes between K groups of the B image
+constexpr int kBSlot = 3 * kGroups * kBLbo;   // 7,680: [tap][group][40][8]
 constexpr int kXFrames = 4;               // frames a super-tile's tape rows can touch
 constexpr int kOutTile = 128 * 160;       // one 128 x 80 bf16 output tile
 constexpr int kProdWarp0 = 6;
@@ -57,12 +62,11 @@ struct ConvSmem {
   static constexpr int a = 0;
   static constexpr int b = a + kStages * kASlot;
   static constexpr int xs = b + kStages * kBSlot;
-  static constexpr int out = xs + kXFrames * 1024;
-  static constexpr int w1 = out + 2 * kOutTile;       // 32 groups x 128 B
-  static constexpr int b2 = w1 + 32 * 128;            // 80 floats
+  static constexpr int out = xs + 2 * kXFrames * 1024;   // two frame buffers
+  static constexpr int b2 = out + 2 * kOutTile;       // 80 floats
   static constexpr int bars = b2 + 320;
-  // full[S], empty[S], x_full, x_empty, tmem_full[2], tmem_empty[2]
-  static constexpr int nbars = 2 * kStages + 2 + 4;
+  // full[S], empty[S], x_full[2], x_empty[2], tmem_full[2], tmem_empty[2]
+  static constexpr int nbars = 2 * kStages + 4 + 4;
   static constexpr int tmem_slot = bars + nbars * 8;
   static constexpr int total = tmem_slot + 16;
 };
@@ -85,57 +89,74 @@ __device__ __forceinline__ uint32_t relu_pack(uint64_t v) {   // {lo, hi} fp32 -
   return cvt_relu_bf16x2(hi, lo);
 }
 
+// conv1 weights travel as a kernel parameter (constant bank): with the chunk loop unrolled every
+// weight is an immediate-offset uniform load feeding FFMA2 directly - no shared-memory broadcast
+// loads (each LDS.128 broadcast costs 4 LSU wavefronts on the pipe the MMA operands also use) and
+// no vector registers.  Layout: 32 channel groups x {w0[8], w1[8], w2[8], bias[8]} fp32.
+struct ConvW1 {
+  unsigned long long v[32 * 16];
+};
+
 // 8 conv1 channels of one tape row: relu(x0 w0 + x1 w1 + x2 w2 + b) -> 8 x bf16 (16 B)
-__device__ __forceinline__ uint4 conv1_item(uint64_t x0, uint64_t x1, uint64_t x2, const ulonglong2 (&w)[8],
+__device__ __forceinline__ uint4 conv1_item(uint64_t x0, uint64_t x1, uint64_t x2, const unsigned long long* w,
                                             uint32_t m) {
-  uint64_t a0 = fma2_u(x0, w[0].x, w[6].x), a1 = fma2_u(x0, w[0].y, w[6].y);
-  uint64_t a2 = fma2_u(x0, w[1].x, w[7].x), a3 = fma2_u(x0, w[1].y, w[7].y);
-  a0 = fma2_u(x1, w[2].x, a0); a1 = fma2_u(x1, w[2].y, a1);
-  a2 = fma2_u(x1, w[3].x, a2); a3 = fma2_u(x1, w[3].y, a3);
-  a0 = fma2_u(x2, w[4].x, a0); a1 = fma2_u(x2, w[4].y, a1);
-  a2 = fma2_u(x2, w[5].x, a2); a3 = fma2_u(x2, w[5].y, a3);
+  uint64_t a0 = fma2_u(x0, w[0], w[12]), a1 = fma2_u(x0, w[1], w[13]);
+  uint64_t a2 = fma2_u(x0, w[2], w[14]), a3 = fma2_u(x0, w[3], w[15]);
+  a0 = fma2_u(x1, w[4], a0); a1 = fma2_u(x1, w[5], a1);
+  a2 = fma2_u(x1, w[6], a2); a3 = fma2_u(x1, w[7], a3);
+  a0 = fma2_u(x2, w[8], a0); a1 = fma2_u(x2, w[9], a1);
+  a2 = fma2_u(x2, w[10], a2); a3 = fma2_u(x2, w[11], a3);
   return make_uint4(relu_pack(a0) & m, relu_pack(a1) & m, relu_pack(a2) & m, relu_pack(a3) & m);
 }
 
-__global__ void __launch_bounds__(kConvThreads, 1)
-vt_conv_bf16_kernel(const float* __restrict__ x, long long n, const uint8_t* __restrict__ w1img,
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
+vt_conv_bf16_kernel(const __grid_constant__ ConvW1 w1c, const float* __restrict__ x, long long n,
                     const float* __restrict__ b2g, const uint8_t* __restrict__ w2img,
-                    __nv_bfloat16* __restrict__ act, long long num_st, int dbg) {
-  // dbg (timing experiments only, results are garbage): 1 = producers skip conv1 math and stores,
-  // 2 = MMA warp skips the MMAs, 4 = epilogue skips TMEM loads / math / stores
+                    __nv_bfloat16* __restrict__ act, long long num_st, int dbg_rt) {
+  // role-ablation flags for timing experiments (build with -DMDC_VT_ABLATE, set MDC_VT_DEBUG; the
+  // results are garbage): 1 = producers skip conv1 math and stores, 2 = MMA warp skips the MMAs,
+  // 4 = epilogue skips TMEM loads / math / stores.  Compiled out of the product build.
+#ifdef MDC_VT_ABLATE
+  const int dbg = dbg_rt;
+#else
+  constexpr int dbg = 0;
+#endif
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ConvSmem::bars);
   uint64_t* full = bars;
   uint64_t* empty = bars + kStages;
-  uint64_t* x_full = bars + 2 * kStages;
-  uint64_t* x_empty = x_full + 1;
-  uint64_t* tmem_full = x_empty + 1;     // [2] accumulator buffers
+  uint64_t* x_full = bars + 2 * kStages;   // [2] frame buffers
+  uint64_t* x_empty = x_full + 2;          // [2]
+  uint64_t* tmem_full = x_empty + 2;       // [2] accumulator buffers
   uint64_t* tmem_empty = tmem_full + 2;  // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + ConvSmem::tmem_slot);
 
   const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
   const long long total_rows = n * 132;
+  const uint32_t rank = cluster_ctarank();                 // 0 = leader (issues the pair's MMAs)
+  // the pair walks super-tiles 2 i and 2 i + 1 in lockstep; a trailing odd one is an all-masked no-op
+  const long long st_first = 2ll * cluster_id_x(), st_step = 2ll * cluster_count_x();
 
   // ---- one-time setup
-  for (int i = tid; i < 32 * 128 / 16; i += kConvThreads)
-    reinterpret_cast<uint4*>(smem + ConvSmem::w1)[i] = reinterpret_cast<const uint4*>(w1img)[i];
   for (int i = tid; i < 80; i += kConvThreads) reinterpret_cast<float*>(smem + ConvSmem::b2)[i] = b2g[i];
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(&full[s], kProdWarps + 1);
+      // own producers + own TMA (+ on the leader: the peer's relay once ITS stage is full)
+      mbar_init(&full[s], kProdWarps + 1 + (rank == 0 ? 1 : 0));
       mbar_init(&empty[s], 1);
     }
-    mbar_init(x_full, 1);
-    mbar_init(x_empty, kProdWarps);
     for (int b = 0; b < 2; ++b) {
+      mbar_init(&x_full[b], 1);
+      mbar_init(&x_empty[b], kProdWarps);
       mbar_init(&tmem_full[b], 1);
-      mbar_init(&tmem_empty[b], 4);
+      mbar_init(&tmem_empty[b], 8);          // (leader's only) 4 epilogue warps of each CTA
     }
     fence_barrier_init();
   }
-  if (warp == 0) tmem_alloc<512>(tmem_slot);
+  if (warp == 0) tmem_alloc_pair<512>(tmem_slot);
   tc_fence_before_sync();
   __syncthreads();
+  cluster_sync_all();
   tc_fence_after_sync();
   const uint32_t tmem = *tmem_slot;
 
@@ -143,60 +164,82 @@ vt_conv_bf16_kernel(const float* __restrict__ x, long long n, const uint8_t* __r
     // ================= TMA: frames of the super-tile + the W2 chunk stream (whole warp loops,
     // one elected lane issues, so every operand stays in uniform registers)
     uint32_t it = 0, k = 0;
-    for (long long st = blockIdx.x; st < num_st; st += gridDim.x, ++k) {
+    const uint8_t* w2half = w2img + (size_t)rank * kBSlot;   // image = [chunk][rank][tap][group][40][8]
+    // frames of super-tile j go to buffer j & 1, one super-tile ahead of the producers
+    auto load_frames = [&](uint32_t j, long long st) {
       const long long f0 = (st * kOutRows) / 132;
       const long long left = n - f0;
-      const uint32_t nf = left < kXFrames ? (uint32_t)left : (uint32_t)kXFrames;
-      mbar_wait(x_empty, (k & 1) ^ 1);
+      const uint32_t nf = left <= 0 ? 0u : (left < kXFrames ? (uint32_t)left : (uint32_t)kXFrames);
+      const uint32_t b = j & 1;
+      mbar_wait(&x_empty[b], ((j >> 1) & 1) ^ 1);
       if (elect_one()) {
-        mbar_arrive_expect_tx(x_full, nf * 1024);
-        bulk_g2s(smem + ConvSmem::xs, x + f0 * 256, nf * 1024, x_full);
+        mbar_arrive_expect_tx(&x_full[b], nf * 1024);
+        if (nf) bulk_g2s(smem + ConvSmem::xs + b * (kXFrames * 1024), x + f0 * 256, nf * 1024, &x_full[b]);
       }
       __syncwarp();
+    };
+    if (st_first < num_st) load_frames(0, st_first + rank);
+    for (long long base = st_first; base < num_st; base += st_step, ++k) {
+      if (base + st_step < num_st) load_frames(k + 1, base + st_step + rank);
       for (int c = 0; c < kChunks; ++c, ++it) {
         const uint32_t s = it % kStages, ph = (it / kStages) & 1;
         mbar_wait(&empty[s], ph ^ 1);
         if (elect_one()) {
           mbar_arrive_expect_tx(&full[s], kBSlot);
-          bulk_g2s(smem + ConvSmem::b + s * kBSlot, w2img + (size_t)c * kBSlot, kBSlot, &full[s]);
+          bulk_g2s(smem + ConvSmem::b + s * kBSlot, w2half + (size_t)c * 2 * kBSlot, kBSlot, &full[s]);
         }
         __syncwarp();
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer: whole warp loops, one elected lane issues
-    const uint32_t idesc = make_idesc_bf16(128, 80);
-    const uint32_t a_base = smem_u32(smem + ConvSmem::a), b_base = smem_u32(smem + ConvSmem::b);
-    constexpr uint32_t hi = smem_desc_hi(128, 0);
+    // ================= MMA issuer (leader CTA; whole warp loops, one elected lane issues) /
+    // relay (peer CTA: forwards "my stage is full" to the leader's barrier)
     uint32_t it = 0, k = 0;
-    for (long long st = blockIdx.x; st < num_st; st += gridDim.x, ++k) {
-      const uint32_t buf = k & 1;
-      const uint32_t acc = tmem + buf * kAccCols;
-      mbar_wait(&tmem_empty[buf], ((k >> 1) & 1) ^ 1);     // epilogue drained this buffer
-      for (int c = 0; c < kChunks; ++c, ++it) {
-        const uint32_t s = it % kStages, ph = (it / kStages) & 1;
-        mbar_wait(&full[s], ph);
-        tc_fence_after_sync();
-        if (elect_one()) {
-          const uint32_t a_lo = smem_desc_lo(a_base + s * kASlot, kALbo);
-          const uint32_t b_lo = smem_desc_lo(b_base + s * kBSlot, kBLbo);
+    if (rank == 0) {
+      const uint32_t idesc = make_idesc_bf16(256, 80);
+      const uint32_t a_base = smem_u32(smem + ConvSmem::a), b_base = smem_u32(smem + ConvSmem::b);
+      constexpr uint32_t hi = smem_desc_hi(128, 0);
+      for (long long base = st_first; base < num_st; base += st_step, ++k) {
+        const uint32_t buf = k & 1;
+        const uint32_t acc = tmem + buf * kAccCols;
+        mbar_wait(&tmem_empty[buf], ((k >> 1) & 1) ^ 1);     // both epilogues drained this buffer
+        mbar_wait_cluster(&tmem_empty[buf], ((k >> 1) & 1) ^ 1);
+        for (int c = 0; c < kChunks; ++c, ++it) {
+          const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+          mbar_wait(&full[s], ph);               // cheap cta-scope spin ...
+          mbar_wait_cluster(&full[s], ph);       // ... then one cluster-scope acquire (the peer's relay)
+          tc_fence_after_sync();
+          if (elect_one()) {
+            const uint32_t a_lo = smem_desc_lo(a_base + s * kASlot, kALbo);
+            const uint32_t b_lo = smem_desc_lo(b_base + s * kBSlot, kBLbo);
 #pragma unroll
-          for (int t = 0; t < kNT; ++t) {
-            if (dbg & 2) continue;
+            for (int t = 0; t < kNT; ++t) {
+              if (dbg & 2) continue;
 #pragma unroll
-            for (int ks = 0; ks < kKC / 16; ++ks) {
+              for (int ks = 0; ks < kKC / 16; ++ks) {
 #pragma unroll
-              for (int j = 0; j < 3; ++j) {
-                const uint32_t ao = ((2 * ks) * kALbo + (128 * t + j) * 16) >> 4;
-                const uint32_t bo = ((j * kGroups + 2 * ks) * kBLbo) >> 4;
-                mma_bf16_ss(acc + t * 80, desc64(a_lo + ao, hi), desc64(b_lo + bo, hi), idesc, (c | ks | j) != 0);
+                for (int j = 0; j < 3; ++j) {
+                  const uint32_t ao = ((2 * ks) * kALbo + (128 * t + j) * 16) >> 4;
+                  const uint32_t bo = ((j * kGroups + 2 * ks) * kBLbo) >> 4;
+                  mma_bf16_ss_pair(acc + t * 80, desc64(a_lo + ao, hi), desc64(b_lo + bo, hi), idesc,
+                                   (c | ks | j) != 0);
+                }
               }
             }
+            mma_commit_pair(&empty[s]);
+            if (c == kChunks - 1) mma_commit_pair(&tmem_full[buf]);
           }
-          mma_commit(&empty[s]);
-          if (c == kChunks - 1) mma_commit(&tmem_full[buf]);
+          __syncwarp();
         }
-        __syncwarp();
+      }
+    } else {
+      for (long long base = st_first; base < num_st; base += st_step) {
+        for (int c = 0; c < kChunks; ++c, ++it) {
+          const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+          mbar_wait(&full[s], ph);
+          if (elect_one()) mbar_arrive_remote(&full[s], 0);
+          __syncwarp();
+        }
       }
     }
   } else if (warp < kProdWarp0) {
@@ -205,8 +248,8 @@ vt_conv_bf16_kernel(const float* __restrict__ x, long long n, const uint8_t* __r
     const bool leader = (warp == 2 && lane == 0);
     const float4* b2s = reinterpret_cast<const float4*>(smem + ConvSmem::b2);
     uint32_t k = 0, tile_ctr = 0;
-    for (long long st = blockIdx.x; st < num_st; st += gridDim.x, ++k) {
-      const long long r0 = st * kOutRows;
+    for (long long base = st_first; base < num_st; base += st_step, ++k) {
+      const long long r0 = (base + rank) * kOutRows;
       const uint32_t buf = k & 1;
       mbar_wait(&tmem_full[buf], (k >> 1) & 1);
       tc_fence_after_sync();
@@ -230,7 +273,10 @@ vt_conv_bf16_kernel(const float* __restrict__ x, long long n, const uint8_t* __r
         if (t == kNT - 1) {                       // whole buffer read: hand it back to the MMA warp
           tc_fence_before_sync();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+          if (lane == 0) {
+            if (rank == 0) mbar_arrive(&tmem_empty[buf]);
+            else mbar_arrive_remote(&tmem_empty[buf], 0);
+          }
         }
         uint8_t* orow = obuf + (q * 32 + lane) * 160;
 #pragma unroll
@@ -260,25 +306,24 @@ vt_conv_bf16_kernel(const float* __restrict__ x, long long n, const uint8_t* __r
     if (leader) bulk_wait<0>();
   } else {
     // ================= conv1 producers: fp32 FMA -> ReLU -> bf16 -> A operand image.
-    // One tape row per thread; a chunk is 16 channels x {I row, Q row}, so each 8-channel weight
-    // set loaded from shared memory is used for both input rows.
+    // One tape row per thread; a chunk is 16 channels x {I row, Q row}; weights come from the
+    // constant bank (uniform registers), inputs stay in registers for the whole super-tile.
     const int pw = warp - kProdWarp0;
     const int row = pw * 32 + lane;
-    const float* xs = reinterpret_cast<const float*>(smem + ConvSmem::xs);
-    const ulonglong2* w1s = reinterpret_cast<const ulonglong2*>(smem + ConvSmem::w1);
     uint32_t it = 0, k = 0;
-    for (long long st = blockIdx.x; st < num_st; st += gridDim.x, ++k) {
-      const long long t0 = st * kOutRows;          // first tape row of this super-tile
+    for (long long base = st_first; base < num_st; base += st_step, ++k) {
+      const long long t0 = (base + rank) * kOutRows;   // first tape row of this super-tile
       const long long f0 = t0 / 132;
       const long long tp = t0 + row;
       const long long f = tp / 132;
       const int p = (int)(tp - f * 132);
       const bool valid = (p >= 2) && (f < n);
       const uint32_t m = valid ? 0xFFFFFFFFu : 0u;
-      mbar_wait(x_full, k & 1);
+      const uint32_t xb = k & 1;
+      mbar_wait(&x_full[xb], (k >> 1) & 1);
       uint64_t xd[2][3];
       {
-        const float* xf = xs + (f - f0) * 256;
+        const float* xf = reinterpret_cast<const float*>(smem + ConvSmem::xs + xb * (kXFrames * 1024)) + (f - f0) * 256;
 #pragma unroll
         for (int r = 0; r < 2; ++r)
 #pragma unroll
@@ -289,19 +334,24 @@ vt_conv_bf16_kernel(const float* __restrict__ x, long long n, const uint8_t* __r
           }
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(x_empty);
-#pragma unroll 1
+      if (lane == 0) mbar_arrive(&x_empty[xb]);
+#pragma unroll
       for (int c = 0; c < kChunks; ++c, ++it) {
         // compute the chunk into registers first: nothing here depends on the stage being free
         uint4 o[kGroups];
 #pragma unroll
         for (int hc = 0; hc < kCC / 8; ++hc) {
           if (dbg & 1) break;
-          ulonglong2 w[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) w[i] = w1s[(c * (kCC / 8) + hc) * 8 + i];
+          const unsigned long long* w = &w1c.v[(c * (kCC / 8) + hc) * 16];
           o[2 * hc] = conv1_item(xd[0][0], xd[0][1], xd[0][2], w, m);
           o[2 * hc + 1] = conv1_item(xd[1][0], xd[1][1], xd[1][2], w, m);
+        }
+        // publish the PREVIOUS chunk now: its stores were issued a whole chunk of math ago, so the
+        // generic->async proxy fence no longer waits on them
+        if (it > 0) {
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&full[(it - 1) % kStages]);
         }
         const uint32_t s = it % kStages, ph = (it / kStages) & 1;
         mbar_wait(&empty[s], ph ^ 1);
@@ -310,18 +360,21 @@ vt_conv_bf16_kernel(const float* __restrict__ x, long long n, const uint8_t* __r
 #pragma unroll
           for (int g = 0; g < kGroups; ++g) *reinterpret_cast<uint4*>(arow + g * kALbo) = o[g];
         }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&full[s]);
       }
+    }
+    if (it > 0) {
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[(it - 1) % kStages]);
     }
   }
 
-  // ---- teardown
+  // ---- teardown (the pair leaves together: the leader's MMAs read the peer's shared memory)
   __syncwarp();
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 0) tmem_dealloc<512>(tmem);
+  cluster_sync_all();
+  if (warp == 0) tmem_dealloc_pair<512>(tmem);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -519,23 +572,24 @@ int pack_vt_bf16(mdc_handle_s* h) {
         img[g * 32 + 16 + e] = w1[512 + ch];
         img[g * 32 + 24 + e] = b1[ch];
       }
-    if (int e = h->vt_w1.reserve(img.size() * 4)) return e;
-    MDC_CUDA(cudaMemcpy(h->vt_w1.ptr, img.data(), img.size() * 4, cudaMemcpyHostToDevice));
+    h->vt_w1_img = img;      // passed by value as a kernel parameter
   }
-  // conv2 image: [chunk][tap][group][out 80][8 k] bf16; chunk c = conv1 channels 16c..16c+15,
-  // group g = 2*(channel half) + input row  (Keras (2,3,256,80) = [r][j][ch][o])
+  // conv2 image: [chunk][pair rank][tap][group][40 out][8 k] bf16; chunk c = conv1 channels
+  // 16c..16c+15, group g = 2*(channel half) + input row, rank h holds output channels 40h..40h+39
+  // (Keras (2,3,256,80) = [r][j][ch][o])
   {
-    std::vector<uint16_t> img((size_t)kChunks * kBSlot / 2);
+    std::vector<uint16_t> img((size_t)kChunks * 2 * kBSlot / 2);
     const float* w2 = h->w[MDC_T_CONV2_K].data();
     for (int c = 0; c < kChunks; ++c)
-      for (int j = 0; j < 3; ++j)
-        for (int g = 0; g < kGroups; ++g)
-          for (int o = 0; o < 80; ++o)
-            for (int e = 0; e < 8; ++e) {
-              const int r = g & 1, ch = c * kCC + (g >> 1) * 8 + e;
-              img[(size_t)c * (kBSlot / 2) + ((size_t)(j * kGroups + g) * 80 + o) * 8 + e] =
-                  f2bf(w2[((size_t)(r * 3 + j) * 256 + ch) * 80 + o]);
-            }
+      for (int hf = 0; hf < 2; ++hf)
+        for (int j = 0; j < 3; ++j)
+          for (int g = 0; g < kGroups; ++g)
+            for (int oo = 0; oo < kBHalf; ++oo)
+              for (int e = 0; e < 8; ++e) {
+                const int r = g & 1, ch = c * kCC + (g >> 1) * 8 + e, o = hf * kBHalf + oo;
+                img[((size_t)(c * 2 + hf) * (kBSlot / 2)) + ((size_t)(j * kGroups + g) * kBHalf + oo) * 8 + e] =
+                    f2bf(w2[((size_t)(r * 3 + j) * 256 + ch) * 80 + o]);
+              }
     if (int e = h->vt_w2_bf16.reserve(img.size() * 2)) return e;
     MDC_CUDA(cudaMemcpy(h->vt_w2_bf16.ptr, img.data(), img.size() * 2, cudaMemcpyHostToDevice));
   }
@@ -565,14 +619,18 @@ int launch_vt_bf16(mdc_handle_s* h, const float* x, int64_t n, float* probs, flo
   if (int e = h->ws_h.reserve((size_t)cap * kVtH * 4)) return e;
   __nv_bfloat16* act = reinterpret_cast<__nv_bfloat16*>(h->ws_act.ptr);
   float* hb = reinterpret_cast<float*>(h->ws_h.ptr);
+  ConvW1 w1c;
+  static_assert(sizeof(ConvW1) == 32 * 32 * sizeof(float), "conv1 image size");
+  memcpy(&w1c, h->vt_w1_img.data(), sizeof(w1c));
   static const int dbg = getenv("MDC_VT_DEBUG") ? atoi(getenv("MDC_VT_DEBUG")) : 0;   // timing experiments
   for (int64_t s = 0; s < n; s += CH) {
     const int64_t m = (n - s) < CH ? (n - s) : CH;
     const long long num_st = (m * 132 + kOutRows - 1) / kOutRows;
-    const unsigned grid_c = (unsigned)(num_st < h->num_sms ? num_st : h->num_sms);
+    const long long pairs_needed = (num_st + 1) / 2, pairs_max = h->num_sms / 2;
+    const unsigned grid_c = 2u * (unsigned)(pairs_needed < pairs_max ? pairs_needed : pairs_max);
     prof_begin(h, stream);
     vt_conv_bf16_kernel<<<grid_c, kConvThreads, ConvSmem::total, stream>>>(
-        x + s * 256, m, reinterpret_cast<const uint8_t*>(h->vt_w1.ptr), reinterpret_cast<const float*>(h->vt_b2.ptr),
+        w1c, x + s * 256, m, reinterpret_cast<const float*>(h->vt_b2.ptr),
         reinterpret_cast<const uint8_t*>(h->vt_w2_bf16.ptr), act, num_st, dbg);
     prof_end(h, stream);
     MDC_CUDA(cudaGetLastError());
