@@ -24,17 +24,26 @@ struct QParams {
   int F, C;
 };
 
-__device__ __forceinline__ int wrap18(int v) { return (v << 14) >> 14; }
+__device__ __forceinline__ int wrap18(int v) {   // sign-extend bit 17 (SGXT)
+  int r;
+  asm("bfe.s32 %0, %1, 0, 18;" : "=r"(r) : "r"(v));
+  return r;
+}
 
 // {m[35], m[28:12]} of the 36-bit a*b + c*d, as a signed 18-bit value.
-// |a*b + c*d| <= 2^35, exact in 64 bits; bit 35 of the 64-bit two's complement pattern is
-// bit 35 of the value mod 2^36.
+// |a*b + c*d| <= 2^35 is exact in 64 bits (two IMAD.WIDE); S = bits [43:12] of the 64-bit two's
+// complement pattern (one funnel shift) carries m[28:12] in S[16:0] and m[35] in S[23] - the low 36
+// bits of the pattern are the value mod 2^36 - so the slice is S with bit 17 replaced by bit 23,
+// sign-extended from bit 17: IMAD.WIDE x2, SHF x2, LOP3, SGXT.
 __device__ __forceinline__ int slice36(int a, int b, int c, int d) {
-  long long m = (long long)a * (long long)b + (long long)c * (long long)d;
-  unsigned lo = (unsigned)((unsigned long long)m >> 12);
-  unsigned hi = (unsigned)((unsigned long long)m >> 32);
-  int top = ((int)(hi << 28)) >> 31;                  // 0 or -1 : replicated bit 35
-  return (int)((lo & 0x1FFFFu) | ((unsigned)top & 0xFFFE0000u));
+  long long m;
+  asm("{\n\t.reg .s64 t;\n\tmul.wide.s32 t, %3, %4;\n\tmad.wide.s32 %0, %1, %2, t;\n\t}"
+      : "=l"(m)
+      : "r"(a), "r"(b), "r"(c), "r"(d));
+  const unsigned S = __funnelshift_r((unsigned)m, (unsigned)((unsigned long long)m >> 32), 12);
+  unsigned x;
+  asm("lop3.b32 %0, %1, %2, 0x20000, 0xE4;" : "=r"(x) : "r"(S >> 6), "r"(S));   // (a & c) | (b & ~c)
+  return wrap18((int)x);
 }
 
 __device__ __forceinline__ int conv18(int a, int w0, int c, int w1, int bias) {
