@@ -311,14 +311,15 @@ int mdc_set_weights_q612(mdc_handle_t h, const int32_t* conv_tab, const int32_t*
     MDC_REQUIRE(in18(dense_tabs[i]), MDC_ERR_INVALID, "dense_tabs[%zu]=%d is not an 18-bit signed value", i, dense_tabs[i]);
   h->q_conv_host.assign(conv_tab, conv_tab + 3 * F);
   h->q_bias_host.assign(dense_bias, dense_bias + C);
-  // pre-skew: image[f][c][iq][s] = tab[2c+iq][128 f + max(s-1,0)]   (dense_layer, sv:336,351-378)
+  // pre-skew: image[f][c][iq][s] = 8 * tab[2c+iq][128 f + max(s-1,0)]   (dense_layer, sv:336,351-378;
+  // the factor 8 positions the product for the kernel's slice36, see q612.cu)
   std::vector<int> img((size_t)F * C * 2 * 128);
   for (int f = 0; f < F; ++f)
     for (int c = 0; c < C; ++c)
       for (int iq = 0; iq < 2; ++iq)
         for (int s = 0; s < 128; ++s)
           img[(((size_t)f * C + c) * 2 + iq) * 128 + s] =
-              dense_tabs[(size_t)(2 * c + iq) * tab + 128 * f + (s > 0 ? s - 1 : 0)];
+              8 * dense_tabs[(size_t)(2 * c + iq) * tab + 128 * f + (s > 0 ? s - 1 : 0)];
   if (int e = h->q_dense.reserve(img.size() * sizeof(int))) return e;
   MDC_CUDA(cudaMemcpy(h->q_dense.ptr, img.data(), img.size() * sizeof(int), cudaMemcpyHostToDevice));
   h->have_q = true;

@@ -30,20 +30,22 @@ __device__ __forceinline__ int wrap18(int v) {   // sign-extend bit 17 (SGXT)
   return r;
 }
 
-// {m[35], m[28:12]} of the 36-bit a*b + c*d, as a signed 18-bit value.
-// |a*b + c*d| <= 2^35 is exact in 64 bits (two IMAD.WIDE); S = bits [43:12] of the 64-bit two's
-// complement pattern (one funnel shift) carries m[28:12] in S[16:0] and m[35] in S[23] - the low 36
-// bits of the pattern are the value mod 2^36 - so the slice is S with bit 17 replaced by bit 23,
-// sign-extended from bit 17: IMAD.WIDE x2, SHF x2, LOP3, SGXT.
-__device__ __forceinline__ int slice36(int a, int b, int c, int d) {
-  long long m;
+// {m[35], m[28:12]} of the 36-bit m = a*b + c*d, as a signed 18-bit value.
+// The weights b, d arrive PRE-MULTIPLIED BY 8 (host side), so the 64-bit M = 8 m (exact: |M| <= 2^38,
+// two IMAD.WIDE) has m[28:12] in the top 17 bits of its low word and m[35] in bit 6 of its high
+// word - the low 39 bits of the two's complement pattern are 8 * (m mod 2^36).  One left shift (on
+// the FMA pipe, as a multiply) and one arithmetic right shift replicate m[35]; one funnel shift
+// glues {m[35] x 15, m[28:12]}.  3 FMA-pipe + 2 ALU-pipe instructions per slice.
+__device__ __forceinline__ int slice36(int a, int b8, int c, int d8) {
+  long long M;
   asm("{\n\t.reg .s64 t;\n\tmul.wide.s32 t, %3, %4;\n\tmad.wide.s32 %0, %1, %2, t;\n\t}"
-      : "=l"(m)
-      : "r"(a), "r"(b), "r"(c), "r"(d));
-  const unsigned S = __funnelshift_r((unsigned)m, (unsigned)((unsigned long long)m >> 32), 12);
-  unsigned x;
-  asm("lop3.b32 %0, %1, %2, 0x20000, 0xE4;" : "=r"(x) : "r"(S >> 6), "r"(S));   // (a & c) | (b & ~c)
-  return wrap18((int)x);
+      : "=l"(M)
+      : "r"(a), "r"(b8), "r"(c), "r"(d8));
+  const unsigned lo = (unsigned)M, hi = (unsigned)((unsigned long long)M >> 32);
+  unsigned t;
+  asm("mul.lo.u32 %0, %1, 33554432;" : "=r"(t) : "r"(hi));     // hi << 25 : bit 31 = m[35]
+  const int sign = (int)t >> 31;
+  return (int)__funnelshift_r(lo, (unsigned)sign, 15);
 }
 
 __device__ __forceinline__ int conv18(int a, int w0, int c, int w1, int bias) {
@@ -204,7 +206,8 @@ int launch_q612(mdc_handle_s* h, const int32_t* x, int64_t n, int32_t* out, int3
   QParams p;
   const int* conv = h->q_conv_host.data();
   const int* bias = h->q_bias_host.data();
-  for (int i = 0; i < 3 * kMaxFilters; ++i) p.conv[i] = i < 3 * h->F ? conv[i] : 0;
+  // w0, w1 pre-multiplied by 8 (see slice36); the conv bias (every third entry) is not
+  for (int i = 0; i < 3 * kMaxFilters; ++i) p.conv[i] = i < 3 * h->F ? (i % 3 == 2 ? conv[i] : conv[i] * 8) : 0;
   for (int i = 0; i < kMaxClasses; ++i) p.bias[i] = i < h->C ? bias[i] : 0;
   p.F = h->F;
   p.C = h->C;

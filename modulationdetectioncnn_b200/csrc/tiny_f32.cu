@@ -6,15 +6,20 @@
 //   y[r][p][f] = relu(xp[r][p]*k0[f] + xp[r][p+1]*k1[f] + b[f]),  p = 0..128, xp[0]=xp[129]=0
 //   z[c]       = relu(sum_{r,p,f} y[r][p][f] * D[(r*129 + p)*F + f][c] + d[c])
 //
-// Mapping: one warp per frame (R frames per pass).  Lane l owns positions p = 4l..4l+3 of
-// both rows -> two coalesced 512 B float4 loads per frame per warp; position 128 (which
-// only needs x[127]) is spread over lanes 0..2F-1, one (row,filter) pair each.  For F*C
-// small enough (F=3,C=3: 72 registers) the Dense rows a lane needs stay in registers for
-// the whole persistent kernel; otherwise they are re-read through L1 once per pass and
-// applied to R frames.  Softmax, argmax and the class histogram are fused in the epilogue.
+// HBM-bound (1,036 B per frame), so the kernel is built around keeping bytes in flight: persistent
+// CTAs, one producer warp streaming blocks of 8R frames into a shared-memory ring with 1-D bulk
+// TMA copies (mbarrier full/empty per stage, ~100 KB in flight per CTA), eight consumer warps
+// taking R frames each per stage.  A consumer warp maps lane l to positions p = 4l..4l+3 of both
+// rows (conflict-free 16-B shared loads); position 128 (which only needs x[127]) is spread over
+// lanes 0..2F-1, one (row,filter) pair each.  The math is packed FFMA2 (two positions per
+// instruction).  For F*C small enough (F=3,C=3: 72 registers) the Dense rows a lane needs stay in
+// registers for the whole kernel; otherwise they live in shared memory.  Softmax, argmax and the
+// class histogram are fused in the epilogue.
 #include "mdc_internal.cuh"
+#include "sm100.cuh"
 
 namespace mdc {
+using namespace sm100;
 
 struct TinyParams {
   float conv[3 * kMaxFilters];   // k0,k1,b per filter
@@ -22,26 +27,83 @@ struct TinyParams {
   int F, C;
 };
 
-__device__ __forceinline__ float4 ldg_stream_f4(const float4* p) {
-  float4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
-               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
-  return r;
+constexpr int kTinyConsumers = 7;                           // consumer warps per CTA (8 warps: 128 regs at 2 CTAs/SM)
+constexpr int kTinyThreads = (kTinyConsumers + 1) * 32;     // + the TMA producer warp
+
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+  return d;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t f2_relu(uint64_t v) {
+  float lo, hi;
+  f2_unpack(v, lo, hi);
+  return f2_pack(fmaxf(lo, 0.f), fmaxf(hi, 0.f));
 }
 
 // dense image (packed on host):
 //   main [r][f][c][128]  entry p = D[(r*129 + p)*F + f][c]            -> float4 per lane
 //   tail [r][f][c]       = D[(r*129 + 128)*F + f][c]                  (position 128)
-template <int F, int C, int R, bool WREG>
-__global__ void __launch_bounds__(256, 2)
+// dynamic shared memory: ring [STAGES][8R frames][256 f32] | (WREG ? nothing : main image) | barriers
+template <int F, int C, int R, int STAGES, bool WREG, int MINB>
+__global__ void __launch_bounds__(kTinyThreads, MINB)
 tiny_f32_kernel(const TinyParams p, const float4* __restrict__ dmain, const float* __restrict__ dtail,
-                const float4* __restrict__ x, long long n, float* __restrict__ probs,
+                const float* __restrict__ x, long long n, float* __restrict__ probs,
                 float* __restrict__ dense, int* __restrict__ cls,
                 unsigned long long* __restrict__ hist) {
-  const int lane = threadIdx.x & 31;
-  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  constexpr int kBlockFrames = kTinyConsumers * R;
+  constexpr int kStageBytes = kBlockFrames * 1024;
+  constexpr int kWBytes = WREG ? 0 : 2 * F * C * 128 * 4;
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* ring = smem;
+  const float4* wsm = reinterpret_cast<const float4*>(smem + STAGES * kStageBytes);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * kStageBytes + kWBytes);
+  uint64_t* empty = full + STAGES;
 
+  const int lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx();
+  const long long nblocks = (n + kBlockFrames - 1) / kBlockFrames;
+
+  if (!WREG) {
+    float4* wdst = reinterpret_cast<float4*>(smem + STAGES * kStageBytes);
+    for (int i = threadIdx.x; i < 2 * F * C * 32; i += kTinyThreads) wdst[i] = __ldg(dmain + i);
+  }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], kTinyConsumers);
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
+
+  if (warp == kTinyConsumers) {
+    // ---- producer: one bulk copy per block of frames
+    uint32_t it = 0;
+    for (long long blk = blockIdx.x; blk < nblocks; blk += gridDim.x, ++it) {
+      const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+      const long long f0 = blk * kBlockFrames;
+      const long long left = n - f0;
+      const uint32_t bytes = (uint32_t)(left < kBlockFrames ? left : kBlockFrames) * 1024u;
+      mbar_wait(&empty[s], ph ^ 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&full[s], bytes);
+        bulk_g2s(ring + s * kStageBytes, x + f0 * 256, bytes, &full[s]);
+      }
+      __syncwarp();
+    }
+    return;
+  }
+
+  // ---- consumers
   float4 w[WREG ? 2 * F * C : 1];
   if (WREG) {
 #pragma unroll
@@ -62,31 +124,50 @@ tiny_f32_kernel(const TinyParams p, const float4* __restrict__ dmain, const floa
   }
   unsigned cnt = 0;
 
-  for (long long f0 = warp * R; f0 < n; f0 += nwarps * R) {
+  uint32_t it = 0;
+  for (long long blk = blockIdx.x; blk < nblocks; blk += gridDim.x, ++it) {
+    const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+    const long long f0 = blk * kBlockFrames + warp * R;
+    mbar_wait(&full[s], ph);
     float4 xi[R], xq[R];
+    {
+      const float4* src = reinterpret_cast<const float4*>(ring + s * kStageBytes) + warp * R * 64;
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const long long f = f0 + r < n ? f0 + r : n - 1;
-      xi[r] = ldg_stream_f4(x + f * 64 + lane);
-      xq[r] = ldg_stream_f4(x + f * 64 + 32 + lane);
+      for (int r = 0; r < R; ++r) {
+        xi[r] = src[r * 64 + lane];
+        xq[r] = src[r * 64 + 32 + lane];
+      }
     }
-    float acc[R][C];
-    float pi[R], pq[R];
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);       // frames are in registers: hand the stage back
+
+    uint64_t acc[R][C];       // {even positions, odd positions} partial sums
+    uint64_t PI01[R], PI23[R], XI01[R], XI23[R], PQ01[R], PQ23[R], XQ01[R], XQ23[R];
+    float tail[R][C];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      pi[r] = __shfl_up_sync(0xffffffffu, xi[r].w, 1);
-      pq[r] = __shfl_up_sync(0xffffffffu, xq[r].w, 1);
-      if (lane == 0) { pi[r] = 0.f; pq[r] = 0.f; }
+      float pi = __shfl_up_sync(0xffffffffu, xi[r].w, 1);
+      float pq = __shfl_up_sync(0xffffffffu, xq[r].w, 1);
+      if (lane == 0) { pi = 0.f; pq = 0.f; }
+      // y[i] = relu(x[i-1] k0 + x[i] k1 + b): pairs (y0,y1) and (y2,y3)
+      PI01[r] = f2_pack(pi, xi[r].x);       PI23[r] = f2_pack(xi[r].y, xi[r].z);
+      XI01[r] = f2_pack(xi[r].x, xi[r].y);  XI23[r] = f2_pack(xi[r].z, xi[r].w);
+      PQ01[r] = f2_pack(pq, xq[r].x);       PQ23[r] = f2_pack(xq[r].y, xq[r].z);
+      XQ01[r] = f2_pack(xq[r].x, xq[r].y);  XQ23[r] = f2_pack(xq[r].z, xq[r].w);
       // position 128: xp[128] = x[127] (lane 31 .w), xp[129] = 0
       const float li = __shfl_sync(0xffffffffu, xi[r].w, 31);
       const float lq = __shfl_sync(0xffffffffu, xq[r].w, 31);
       const float yt = fmaxf(fmaf(tr ? lq : li, tk0, tb), 0.f);
 #pragma unroll
-      for (int c = 0; c < C; ++c) acc[r][c] = (lane < 2 * F) ? yt * tw[c] : 0.f;
+      for (int c = 0; c < C; ++c) {
+        tail[r][c] = (lane < 2 * F) ? yt * tw[c] : 0.f;
+        acc[r][c] = 0ull;
+      }
     }
 #pragma unroll
     for (int k = 0; k < F; ++k) {
-      const float k0 = p.conv[3 * k], k1 = p.conv[3 * k + 1], b = p.conv[3 * k + 2];
+      const uint64_t K0 = f2_pack(p.conv[3 * k], p.conv[3 * k]), K1 = f2_pack(p.conv[3 * k + 1], p.conv[3 * k + 1]);
+      const uint64_t B = f2_pack(p.conv[3 * k + 2], p.conv[3 * k + 2]);
       float4 wi[C], wq[C];
 #pragma unroll
       for (int c = 0; c < C; ++c) {
@@ -94,28 +175,23 @@ tiny_f32_kernel(const TinyParams p, const float4* __restrict__ dmain, const floa
           wi[c] = w[(0 * F + k) * C + c];
           wq[c] = w[(1 * F + k) * C + c];
         } else {
-          wi[c] = __ldg(dmain + ((0 * F + k) * C + c) * 32 + lane);
-          wq[c] = __ldg(dmain + ((1 * F + k) * C + c) * 32 + lane);
+          wi[c] = wsm[((0 * F + k) * C + c) * 32 + lane];
+          wq[c] = wsm[((1 * F + k) * C + c) * 32 + lane];
         }
       }
 #pragma unroll
       for (int r = 0; r < R; ++r) {
-        float yi[4], yq[4];
-        yi[0] = fmaxf(fmaf(pi[r], k0, fmaf(xi[r].x, k1, b)), 0.f);
-        yi[1] = fmaxf(fmaf(xi[r].x, k0, fmaf(xi[r].y, k1, b)), 0.f);
-        yi[2] = fmaxf(fmaf(xi[r].y, k0, fmaf(xi[r].z, k1, b)), 0.f);
-        yi[3] = fmaxf(fmaf(xi[r].z, k0, fmaf(xi[r].w, k1, b)), 0.f);
-        yq[0] = fmaxf(fmaf(pq[r], k0, fmaf(xq[r].x, k1, b)), 0.f);
-        yq[1] = fmaxf(fmaf(xq[r].x, k0, fmaf(xq[r].y, k1, b)), 0.f);
-        yq[2] = fmaxf(fmaf(xq[r].y, k0, fmaf(xq[r].z, k1, b)), 0.f);
-        yq[3] = fmaxf(fmaf(xq[r].z, k0, fmaf(xq[r].w, k1, b)), 0.f);
+        const uint64_t yi01 = f2_relu(f2_fma(K0, PI01[r], f2_fma(K1, XI01[r], B)));
+        const uint64_t yi23 = f2_relu(f2_fma(K0, PI23[r], f2_fma(K1, XI23[r], B)));
+        const uint64_t yq01 = f2_relu(f2_fma(K0, PQ01[r], f2_fma(K1, XQ01[r], B)));
+        const uint64_t yq23 = f2_relu(f2_fma(K0, PQ23[r], f2_fma(K1, XQ23[r], B)));
 #pragma unroll
         for (int c = 0; c < C; ++c) {
-          float a = acc[r][c];
-          a = fmaf(yi[0], wi[c].x, a); a = fmaf(yi[1], wi[c].y, a);
-          a = fmaf(yi[2], wi[c].z, a); a = fmaf(yi[3], wi[c].w, a);
-          a = fmaf(yq[0], wq[c].x, a); a = fmaf(yq[1], wq[c].y, a);
-          a = fmaf(yq[2], wq[c].z, a); a = fmaf(yq[3], wq[c].w, a);
+          uint64_t a = acc[r][c];
+          a = f2_fma(yi01, f2_pack(wi[c].x, wi[c].y), a);
+          a = f2_fma(yi23, f2_pack(wi[c].z, wi[c].w), a);
+          a = f2_fma(yq01, f2_pack(wq[c].x, wq[c].y), a);
+          a = f2_fma(yq23, f2_pack(wq[c].z, wq[c].w), a);
           acc[r][c] = a;
         }
       }
@@ -125,7 +201,9 @@ tiny_f32_kernel(const TinyParams p, const float4* __restrict__ dmain, const floa
       float z[C];
 #pragma unroll
       for (int c = 0; c < C; ++c) {
-        float a = acc[r][c];
+        float lo, hi;
+        f2_unpack(acc[r][c], lo, hi);
+        float a = (lo + hi) + tail[r][c];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
         z[c] = fmaxf(a + p.bias[c], 0.f);
@@ -136,23 +214,31 @@ tiny_f32_kernel(const TinyParams p, const float4* __restrict__ dmain, const floa
         float m = z[0];
 #pragma unroll
         for (int c = 1; c < C; ++c) if (z[c] > m) { m = z[c]; best = c; }
-        float e[C], s = 0.f;
+        float e[C], sum = 0.f;
 #pragma unroll
-        for (int c = 0; c < C; ++c) { e[c] = expf(z[c] - m); s += e[c]; }
-        const float inv = 1.0f / s;
-        if (lane == 0) {
+        for (int c = 0; c < C; ++c) { e[c] = expf(z[c] - m); sum += e[c]; }
+        const float inv = 1.0f / sum;
+        // lane c writes class c: one coalesced store per output instead of C single-lane stores
+        float zsel = z[0], psel = e[0] * inv;
 #pragma unroll
-          for (int c = 0; c < C; ++c) {
-            if (dense) dense[f * C + c] = z[c];
-            if (probs) probs[f * C + c] = e[c] * inv;
-          }
-          if (cls) cls[f] = best;
+        for (int c = 1; c < C; ++c) if (lane == c) { zsel = z[c]; psel = e[c] * inv; }
+        if (lane < C) {
+          if (dense) dense[f * C + lane] = zsel;
+          if (probs) probs[f * C + lane] = psel;
         }
+        if (lane == 0 && cls) cls[f] = best;
         cnt += (lane == best);
       }
     }
   }
   if (hist && lane < C && cnt) atomicAdd(hist + lane, (unsigned long long)cnt);
+}
+
+__device__ __forceinline__ float4 ldg_stream_f4(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
 }
 
 // Any F<=16, C<=16 (runtime loops; slow path for shapes without a specialisation).
@@ -274,11 +360,34 @@ int launch_tiny_f32(mdc_handle_s* h, const float* x, int64_t n, float* probs, fl
     long long max_blocks = (long long)h->num_sms * 2 * 4;
     return (unsigned)(blocks > max_blocks ? max_blocks : blocks);
   };
+  // variant selection (MDC_TINY_VARIANT, tuning aid): 1 (default) = Dense rows in shared memory,
+  // 3 CTAs/SM; 0 = Dense rows in registers (F=3) / 2 CTAs/SM.  Measured on B200 (2^21 frames):
+  // F=3: 2.63e9 vs 2.55e9 frames/s, F=10: 1.25e9 vs 1.21e9.
+  static const int variant = getenv("MDC_TINY_VARIANT") ? atoi(getenv("MDC_TINY_VARIANT")) : 1;
+  auto ring_grid = [&](int R, int ctas_per_sm) {
+    const long long nblocks = (n + kTinyConsumers * R - 1) / (kTinyConsumers * R);
+    const long long max_blocks = (long long)h->num_sms * ctas_per_sm;
+    return (unsigned)(nblocks > max_blocks ? max_blocks : nblocks);
+  };
+#define MDC_TINY_LAUNCH(F_, C_, R_, S_, WREG_, MINB_)                                                        \
+  do {                                                                                                      \
+    constexpr int smem_ = S_ * kTinyConsumers * R_ * 1024 + (WREG_ ? 0 : 2 * F_ * C_ * 128 * 4) + 2 * S_ * 8; \
+    static bool attr_ = false;                                                                              \
+    if (!attr_) {                                                                                           \
+      MDC_CUDA(cudaFuncSetAttribute(tiny_f32_kernel<F_, C_, R_, S_, WREG_, MINB_>,                          \
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, smem_));                   \
+      attr_ = true;                                                                                         \
+    }                                                                                                       \
+    tiny_f32_kernel<F_, C_, R_, S_, WREG_, MINB_><<<ring_grid(R_, MINB_), kTinyThreads, smem_, stream>>>(   \
+        p, dm, dt, x, n, probs, dense, cls, hist);                                                          \
+  } while (0)
   prof_begin(h, stream);
   if (F == 3 && C == 3) {
-    tiny_f32_kernel<3, 3, 1, true><<<grid(1), threads, 0, stream>>>(p, dm, dt, x4, n, probs, dense, cls, hist);
+    if (variant == 1) MDC_TINY_LAUNCH(3, 3, 2, 4, false, 3);
+    else MDC_TINY_LAUNCH(3, 3, 1, 12, true, 2);
   } else if (F == 10 && C == 3) {
-    tiny_f32_kernel<10, 3, 4, false><<<grid(4), threads, 0, stream>>>(p, dm, dt, x4, n, probs, dense, cls, hist);
+    if (variant == 1) MDC_TINY_LAUNCH(10, 3, 2, 3, false, 3);
+    else MDC_TINY_LAUNCH(10, 3, 2, 4, false, 2);
   } else {
     tiny_f32_generic_kernel<<<grid(1), threads, 0, stream>>>(
         p, reinterpret_cast<const float*>(h->tiny_dense.ptr), dt, x4, n, probs, dense, cls, hist);
