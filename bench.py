@@ -39,6 +39,9 @@ METRIC = "cnn2_frames_per_sec"
 UNIT = "frames/s"
 
 
+_emit = print
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -152,7 +155,7 @@ def run_reference(args):
     dt = time.perf_counter() - t
     v = n * args.steps / dt
     sample = f"{n} frames per step (bounded sample of the {BATCH}-frame batch), torch-CPU stand-in for Keras/TF-CPU predict"
-    print(json.dumps({
+    _emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -294,8 +297,13 @@ def run_ours(args):
     k_avg_ms = kms / max(klaunches, 1)
     achieved = flops_launch / (k_avg_ms * 1e-3) / 1e12 if klaunches else None
     peak = peaks["bf16_tflops_sustained"] if tensor else None
+    # DRAM bytes of one conv-kernel launch at 65,536 frames, from the ncu --set full capture summarised in
+    # profiles/r01_ncu_vt_bf16.md (dram__bytes_read.sum + dram__bytes_write.sum = 0.068 + 1.325 GB; the
+    # algorithmic bytes are 65536 x (1024 in + 21120 out) = 1.451 GB)
+    traffic = 1.393e9 if (tensor and batch == BATCH) else None
     roofline = {"bound": "tensor", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": (achieved / peak) if (achieved and peak) else None, "traffic": None,
+                "frac": (achieved / peak) if (achieved and peak) else None, "traffic": traffic,
+                "frac_of_burst_peak": (achieved / peaks["bf16_tflops"]) if (achieved and tensor) else None,
                 "peak_source": peaks["source"] + (" (bf16 sustained)" if tensor else ""),
                 "launches": klaunches, "avg_launch_ms": k_avg_ms,
                 "algorithmic_flop_per_frame": VT_CONV_FLOP_PER_FRAME,
@@ -338,7 +346,7 @@ def run_ours(args):
         result["cpu_baseline"] = cpu_vt_baseline(weights)
         result["other_paths"] = other_paths(torch, dev, peaks, _lib)
     if rank == 0:
-        print(json.dumps(result))
+        _emit(json.dumps(result))
     if dist_on:
         dist.barrier()
         dist.destroy_process_group()
@@ -419,10 +427,18 @@ def main():
     ap.add_argument("--skip-other", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    # stdout carries exactly ONE JSON line: native libraries (NCCL prints its version banner to fd 1)
+    # are pointed at stderr for the duration of the run
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    global _emit
+    _emit = lambda line: os.write(real_stdout, (line + "\n").encode())
     if args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)
+    sys.stdout.flush()
 
 
 if __name__ == "__main__":

@@ -1,6 +1,8 @@
 // C-ABI entry points of libmdc.so (see include/mdc.h) and the host-buffer pipeline.
 #include <string.h>
 
+#include <mutex>
+
 #include "mdc_internal.cuh"
 
 namespace mdc {
@@ -395,20 +397,41 @@ int mdc_fwht_i32(const int32_t* in_dev, int32_t* out_dev, int64_t n_spectra, int
   return launch_fwht(in_dev, out_dev, n_spectra, log2_npt, ordering, (cudaStream_t)stream);
 }
 
+// streams and device slots of the FWHT host pipeline, created once per device and reused (a
+// cudaMalloc/cudaFree pair per call costs more than the transform)
+namespace {
+struct FwhtPipe {
+  static constexpr int S = 3;
+  cudaStream_t st[S] = {};
+  void* buf[S] = {};
+  size_t bytes = 0;
+  bool ready = false;
+};
+std::mutex g_fwht_mu;
+FwhtPipe g_fwht_pipe[16];
+}  // namespace
+
 int mdc_fwht_i32_host(const int32_t* in_host, int32_t* out_host, int64_t n_spectra, int log2_npt, int ordering,
                       int device) {
   MDC_REQUIRE(log2_npt >= 5 && log2_npt <= 13, MDC_ERR_UNSUPPORTED, "log2_npt=%d outside 5..13", log2_npt);
+  MDC_REQUIRE(ordering == MDC_FWHT_NATURAL || ordering == MDC_FWHT_SEQUENCY, MDC_ERR_INVALID, "ordering %d", ordering);
   MDC_REQUIRE(n_spectra >= 0 && (n_spectra == 0 || (in_host && out_host)), MDC_ERR_INVALID, "bad buffers");
+  MDC_REQUIRE(device >= 0 && device < 16, MDC_ERR_INVALID, "device %d", device);
   if (n_spectra == 0) return MDC_OK;
   MDC_CUDA(cudaSetDevice(device));
+  std::lock_guard<std::mutex> lock(g_fwht_mu);
+  FwhtPipe& P = g_fwht_pipe[device];
+  constexpr int S = FwhtPipe::S;
   const size_t N = (size_t)1 << log2_npt;
-  const int64_t chunk = ((int64_t)16 << 20) / (int64_t)(N * 4) > 0 ? ((int64_t)16 << 20) / (int64_t)(N * 4) : 1;
-  constexpr int S = 3;
-  cudaStream_t st[S];
-  void* buf[S];
-  for (int k = 0; k < S; ++k) {
-    MDC_CUDA(cudaStreamCreateWithFlags(&st[k], cudaStreamNonBlocking));
-    MDC_CUDA(cudaMalloc(&buf[k], (size_t)chunk * N * 4));
+  const size_t slot_bytes = (size_t)16 << 20;                       // 16 MiB per slot
+  const int64_t chunk = (int64_t)(slot_bytes / (N * 4));
+  if (!P.ready) {
+    for (int k = 0; k < S; ++k) {
+      MDC_CUDA(cudaStreamCreateWithFlags(&P.st[k], cudaStreamNonBlocking));
+      MDC_CUDA(cudaMalloc(&P.buf[k], slot_bytes));
+    }
+    P.bytes = slot_bytes;
+    P.ready = true;
   }
   int rc = MDC_OK;
   int64_t i = 0;
@@ -416,18 +439,16 @@ int mdc_fwht_i32_host(const int32_t* in_host, int32_t* out_host, int64_t n_spect
     const int k = (int)(i % S);
     const int64_t m = (n_spectra - s) < chunk ? (n_spectra - s) : chunk;
     // a slot's stream is in-order: H2D -> kernel -> D2H; the three slots overlap each other
-    cudaMemcpyAsync(buf[k], in_host + s * N, (size_t)m * N * 4, cudaMemcpyHostToDevice, st[k]);
-    rc = launch_fwht((const int32_t*)buf[k], (int32_t*)buf[k], m, log2_npt, ordering, st[k]);
-    cudaMemcpyAsync(out_host + s * N, buf[k], (size_t)m * N * 4, cudaMemcpyDeviceToHost, st[k]);
+    MDC_CUDA(cudaMemcpyAsync(P.buf[k], in_host + s * N, (size_t)m * N * 4, cudaMemcpyHostToDevice, P.st[k]));
+    rc = launch_fwht((const int32_t*)P.buf[k], (int32_t*)P.buf[k], m, log2_npt, ordering, P.st[k]);
+    MDC_CUDA(cudaMemcpyAsync(out_host + s * N, P.buf[k], (size_t)m * N * 4, cudaMemcpyDeviceToHost, P.st[k]));
   }
   for (int k = 0; k < S; ++k) {
-    cudaError_t e = cudaStreamSynchronize(st[k]);
+    cudaError_t e = cudaStreamSynchronize(P.st[k]);
     if (e != cudaSuccess && rc == MDC_OK) {
       set_error("fwht host pipeline: %s", cudaGetErrorString(e));
       rc = MDC_ERR_CUDA;
     }
-    cudaStreamDestroy(st[k]);
-    cudaFree(buf[k]);
   }
   return rc;
 }
