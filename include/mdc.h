@@ -54,7 +54,8 @@ enum {
 enum {
   MDC_MODE_FP32 = 0,   /* fp32 FMA on CUDA cores (parity mode, <=1e-5 of the fp64 oracle) */
   MDC_MODE_BF16 = 1,   /* VT-CNN2 only: bf16 operands, fp32 accumulate, tcgen05 tensor cores */
-  MDC_MODE_TF32X3 = 2, /* VT-CNN2 only: reserved (3xTF32 split), not implemented yet */
+  MDC_MODE_TF32X3 = 2, /* VT-CNN2 only: every fp32 operand split into tf32 hi + lo, three tcgen05 kind::tf32
+                          MMAs per product; fp32-level accuracy (<=1e-5 of the fp64 oracle) on tensor cores */
   MDC_MODE_Q612 = 3    /* TinyCNN2 only: bit-exact 18-bit Q6.12 SystemVerilog datapath */
 };
 

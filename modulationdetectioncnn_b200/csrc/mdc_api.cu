@@ -229,8 +229,8 @@ int mdc_create(int model_kind, int filters, int classes, int mode, int device, m
     MDC_REQUIRE(mode == MDC_MODE_FP32 || mode == MDC_MODE_Q612, MDC_ERR_INVALID,
                 "TinyCNN2 supports MDC_MODE_FP32 and MDC_MODE_Q612, not mode %d", mode);
   } else {
-    MDC_REQUIRE(mode == MDC_MODE_FP32 || mode == MDC_MODE_BF16, MDC_ERR_UNSUPPORTED,
-                "VT-CNN2 supports MDC_MODE_FP32 and MDC_MODE_BF16 (mode %d not implemented)", mode);
+    MDC_REQUIRE(mode == MDC_MODE_FP32 || mode == MDC_MODE_BF16 || mode == MDC_MODE_TF32X3, MDC_ERR_INVALID,
+                "VT-CNN2 supports MDC_MODE_FP32, MDC_MODE_BF16 and MDC_MODE_TF32X3, not mode %d", mode);
   }
   int ndev = 0;
   MDC_CUDA(cudaGetDeviceCount(&ndev));
@@ -249,7 +249,8 @@ int mdc_create(int model_kind, int filters, int classes, int mode, int device, m
   h->num_sms = prop.multiProcessorCount;
   h->dominant_kernel = model_kind == MDC_MODEL_TINY
                            ? (mode == MDC_MODE_Q612 ? "q612_kernel" : "tiny_f32_kernel")
-                           : (mode == MDC_MODE_FP32 ? "sgemm_bias_act_kernel(conv2)" : "vt_conv_bf16_kernel");
+                           : (mode == MDC_MODE_FP32 ? "sgemm_bias_act_kernel(conv2)"
+                                                   : (mode == MDC_MODE_BF16 ? "vt_conv_kernel<bf16>" : "vt_conv_kernel<tf32x3>"));
   *out = h;
   return MDC_OK;
 }

@@ -1,4 +1,6 @@
-// VT-CNN2 forward on the sm_100a tensor cores (MDC_MODE_BF16): bf16 operands, fp32 accumulate.
+// VT-CNN2 forward on the sm_100a tensor cores: MDC_MODE_BF16 (bf16 operands, fp32 accumulate) and
+// MDC_MODE_TF32X3 (every fp32 operand split into tf32 hi + lo, three kind::tf32 MMAs per product:
+// hi*hi + hi*lo + lo*hi - fp32-level accuracy, <= 1e-5 of the fp64 oracle, at ~1/6 of the bf16 rate).
 //
 // Layer stack: /root/reference/examples-master/modulation_recognition/
 // RML2016.10a_VTCNN2_example.ipynb:231-243 (shapes :194-216); Dropout = identity.
@@ -41,16 +43,10 @@ void vt_permute_w3(const mdc_handle_s* h, std::vector<float>& out);
 constexpr int kNT = 3;                    // accumulator tiles (128 rows x 80 cols) per super-tile
 constexpr int kTapeRows = 128 * kNT;      // 384 tape rows staged per super-tile
 constexpr int kOutRows = kTapeRows - 2;   // 382 conv2 rows produced per super-tile (2-row halo)
-constexpr int kCC = 16;                   // conv1 channels per pipeline chunk ...
-constexpr int kKC = 2 * kCC;              // ... x 2 input rows (I, Q) = 32 K values = two UMMA K steps
-constexpr int kGroups = kKC / 8;          // 8-value K groups per chunk: g = 2 * (channel half) + row
-constexpr int kChunks = 256 / kCC;        // 16 chunks per super-tile
-constexpr int kStages = 5;
+constexpr int kGroups = 4;                // 16-B K groups per chunk image: g = 2 * (channel block) + input row
 constexpr int kALbo = kTapeRows * 16;     // bytes between K groups of the A image
-constexpr int kASlot = kGroups * kALbo;   // 24,576
 constexpr int kBHalf = 40;                // W2 output channels held by each CTA of the pair
 constexpr int kBLbo = kBHalf * 16;        // bytes between K groups of the B image
-constexpr int kBSlot = 3 * kGroups * kBLbo;   // 7,680: [tap][group][40][8]
 constexpr int kXFrames = 4;               // frames a super-tile's tape rows can touch
 constexpr int kOutTile = 128 * 160;       // one 128 x 80 bf16 output tile
 constexpr int kProdWarp0 = 6;
@@ -58,19 +54,33 @@ constexpr int kProdWarps = kTapeRows / 32;             // 12: one tape row per p
 constexpr int kConvThreads = (kProdWarp0 + kProdWarps) * 32;   // TMA, MMA, 4 epilogue, 12 producers
 constexpr int kAccCols = kNT * 80;        // TMEM columns per accumulator buffer (two buffers)
 
-struct ConvSmem {
+// A chunk is kCC conv1 channels x {I row, Q row} = two UMMA K steps of two 16-B groups:
+//   bf16:   16 channels, 8 per group, one image        (K step = 16 values)
+//   tf32x3:  8 channels, 4 per group, hi and lo images  (K step =  8 values)
+template <bool TF32>
+struct ConvCfg {
+  static constexpr int kCC = TF32 ? 8 : 16;
+  static constexpr int kPerGroup = TF32 ? 4 : 8;
+  static constexpr int kImgs = TF32 ? 2 : 1;
+  static constexpr int kChunks = 256 / kCC;
+  static constexpr int kStages = TF32 ? 3 : 5;
+  static constexpr int kAImg = kGroups * kALbo;            // 24,576
+  static constexpr int kASlot = kImgs * kAImg;
+  static constexpr int kBImg = 3 * kGroups * kBLbo;        // 7,680: [tap][group][40][16 B]
+  static constexpr int kBSlot = kImgs * kBImg;
+  // shared memory map
   static constexpr int a = 0;
   static constexpr int b = a + kStages * kASlot;
   static constexpr int xs = b + kStages * kBSlot;
-  static constexpr int out = xs + 2 * kXFrames * 1024;   // two frame buffers
-  static constexpr int b2 = out + 2 * kOutTile;       // 80 floats
+  static constexpr int out = xs + 2 * kXFrames * 1024;     // two frame buffers before it
+  static constexpr int b2 = out + (TF32 ? 0 : 2 * kOutTile);   // bf16 only: two staged output tiles
   static constexpr int bars = b2 + 320;
   // full[S], empty[S], x_full[2], x_empty[2], tmem_full[2], tmem_empty[2]
   static constexpr int nbars = 2 * kStages + 4 + 4;
   static constexpr int tmem_slot = bars + nbars * 8;
   static constexpr int total = tmem_slot + 16;
 };
-static_assert(ConvSmem::total <= 232448, "conv kernel shared memory exceeds 227 KB");
+static_assert(ConvCfg<false>::total <= 232448 && ConvCfg<true>::total <= 232448, "conv kernel shared memory exceeds 227 KB");
 static_assert(2 * kAccCols <= 512, "accumulators exceed TMEM");
 
 __device__ __forceinline__ uint64_t pack_dup(float v) {
@@ -109,10 +119,36 @@ __device__ __forceinline__ uint4 conv1_item(uint64_t x0, uint64_t x1, uint64_t x
   return make_uint4(relu_pack(a0) & m, relu_pack(a1) & m, relu_pack(a2) & m, relu_pack(a3) & m);
 }
 
+// 4 conv1 channels of one tape row in fp32, split for 3xTF32: hi = value truncated to tf32 (what the
+// tensor core reads of an fp32 operand), lo = value - hi (exact)
+__device__ __forceinline__ void conv1_quad(uint64_t x0, uint64_t x1, uint64_t x2, const unsigned long long* w, int q,
+                                           uint32_t m, uint4& hi, uint4& lo) {
+  uint64_t a0 = fma2_u(x0, w[2 * q], w[12 + 2 * q]), a1 = fma2_u(x0, w[2 * q + 1], w[13 + 2 * q]);
+  a0 = fma2_u(x1, w[4 + 2 * q], a0); a1 = fma2_u(x1, w[5 + 2 * q], a1);
+  a0 = fma2_u(x2, w[8 + 2 * q], a0); a1 = fma2_u(x2, w[9 + 2 * q], a1);
+  float v[4];
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(v[0]), "=f"(v[1]) : "l"(a0));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(v[2]), "=f"(v[3]) : "l"(a1));
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float r = __uint_as_float(__float_as_uint(fmaxf(v[i], 0.f)) & m);
+    h[i] = __float_as_uint(r) & 0xFFFFE000u;
+    l[i] = __float_as_uint(r - __uint_as_float(h[i]));
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// act0/act1: bf16 mode -> act0 = bf16 [rows][80]; tf32x3 mode -> act0 = hi, act1 = lo, fp32 [rows][80]
+template <bool TF32>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
-vt_conv_bf16_kernel(const __grid_constant__ ConvW1 w1c, const float* __restrict__ x, long long n,
-                    const float* __restrict__ b2g, const uint8_t* __restrict__ w2img,
-                    __nv_bfloat16* __restrict__ act, long long num_st, int dbg_rt) {
+vt_conv_kernel(const __grid_constant__ ConvW1 w1c, const float* __restrict__ x, long long n,
+               const float* __restrict__ b2g, const uint8_t* __restrict__ w2img,
+               void* __restrict__ act0, void* __restrict__ act1, long long num_st, int dbg_rt) {
+  using ConvSmem = ConvCfg<TF32>;
+  constexpr int kStages = ConvSmem::kStages, kChunks = ConvSmem::kChunks;
+  constexpr int kASlot = ConvSmem::kASlot, kBSlot = ConvSmem::kBSlot, kAImg = ConvSmem::kAImg, kBImg = ConvSmem::kBImg;
   // role-ablation flags for timing experiments (build with -DMDC_VT_ABLATE, set MDC_VT_DEBUG; the
   // results are garbage): 1 = producers skip conv1 math and stores, 2 = MMA warp skips the MMAs,
   // 4 = epilogue skips TMEM loads / math / stores.  Compiled out of the product build.
@@ -164,7 +200,7 @@ vt_conv_bf16_kernel(const __grid_constant__ ConvW1 w1c, const float* __restrict_
     // ================= TMA: frames of the super-tile + the W2 chunk stream (whole warp loops,
     // one elected lane issues, so every operand stays in uniform registers)
     uint32_t it = 0, k = 0;
-    const uint8_t* w2half = w2img + (size_t)rank * kBSlot;   // image = [chunk][rank][tap][group][40][8]
+    const uint8_t* w2half = w2img + (size_t)rank * kBSlot;   // image = [chunk][rank][hi/lo][tap][group][40][16 B]
     // frames of super-tile j go to buffer j & 1, one super-tile ahead of the producers
     auto load_frames = [&](uint32_t j, long long st) {
       const long long f0 = (st * kOutRows) / 132;
@@ -196,7 +232,7 @@ vt_conv_bf16_kernel(const __grid_constant__ ConvW1 w1c, const float* __restrict_
     // relay (peer CTA: forwards "my stage is full" to the leader's barrier)
     uint32_t it = 0, k = 0;
     if (rank == 0) {
-      const uint32_t idesc = make_idesc_bf16(256, 80);
+      const uint32_t idesc = TF32 ? make_idesc_tf32(256, 80) : make_idesc_bf16(256, 80);
       const uint32_t a_base = smem_u32(smem + ConvSmem::a), b_base = smem_u32(smem + ConvSmem::b);
       constexpr uint32_t hi = smem_desc_hi(128, 0);
       for (long long base = st_first; base < num_st; base += st_step, ++k) {
@@ -216,13 +252,22 @@ vt_conv_bf16_kernel(const __grid_constant__ ConvW1 w1c, const float* __restrict_
             for (int t = 0; t < kNT; ++t) {
               if (dbg & 2) continue;
 #pragma unroll
-              for (int ks = 0; ks < kKC / 16; ++ks) {
+              for (int ks = 0; ks < 2; ++ks) {
 #pragma unroll
                 for (int j = 0; j < 3; ++j) {
                   const uint32_t ao = ((2 * ks) * kALbo + (128 * t + j) * 16) >> 4;
                   const uint32_t bo = ((j * kGroups + 2 * ks) * kBLbo) >> 4;
-                  mma_bf16_ss_pair(acc + t * 80, desc64(a_lo + ao, hi), desc64(b_lo + bo, hi), idesc,
-                                   (c | ks | j) != 0);
+                  if (!TF32) {
+                    mma_bf16_ss_pair(acc + t * 80, desc64(a_lo + ao, hi), desc64(b_lo + bo, hi), idesc,
+                                     (c | ks | j) != 0);
+                  } else {
+                    // small cross terms first, then hi*hi
+                    constexpr uint32_t al = kAImg >> 4, bl = kBImg >> 4;   // offsets of the lo images
+                    mma_tf32_ss_pair(acc + t * 80, desc64(a_lo + ao + al, hi), desc64(b_lo + bo, hi), idesc,
+                                     (c | ks | j) != 0);
+                    mma_tf32_ss_pair(acc + t * 80, desc64(a_lo + ao, hi), desc64(b_lo + bo + bl, hi), idesc, 1);
+                    mma_tf32_ss_pair(acc + t * 80, desc64(a_lo + ao, hi), desc64(b_lo + bo, hi), idesc, 1);
+                  }
                 }
               }
             }
@@ -243,7 +288,8 @@ vt_conv_bf16_kernel(const __grid_constant__ ConvW1 w1c, const float* __restrict_
       }
     }
   } else if (warp < kProdWarp0) {
-    // ================= epilogue: TMEM -> +bias, ReLU, bf16 -> smem tile -> bulk store
+    // ================= epilogue: TMEM -> +bias, ReLU -> bf16 tile in smem -> bulk store (bf16 mode)
+    // or -> tf32 hi / lo fp32 rows straight to global (3xTF32 mode: the mainloop is 6x longer)
     const int q = warp & 3;                      // TMEM lane quarter this warp may read
     const bool leader = (warp == 2 && lane == 0);
     const float4* b2s = reinterpret_cast<const float4*>(smem + ConvSmem::b2);
@@ -256,8 +302,10 @@ vt_conv_bf16_kernel(const __grid_constant__ ConvW1 w1c, const float* __restrict_
 #pragma unroll 1
       for (int t = 0; t < kNT; ++t, ++tile_ctr) {
         uint8_t* obuf = smem + ConvSmem::out + (tile_ctr & 1) * kOutTile;
-        if (leader) bulk_wait_read<1>();          // the store issued two tiles ago has drained obuf
-        named_bar_sync(1, 128);
+        if (!TF32) {
+          if (leader) bulk_wait_read<1>();        // the store issued two tiles ago has drained obuf
+          named_bar_sync(1, 128);
+        }
         uint32_t v[80];
         if (!(dbg & 4)) {
 #pragma unroll
@@ -278,6 +326,32 @@ vt_conv_bf16_kernel(const __grid_constant__ ConvW1 w1c, const float* __restrict_
             else mbar_arrive_remote(&tmem_empty[buf], 0);
           }
         }
+        const long long row_lo = r0 + 128 * t;
+        long long rows = kOutRows - 128 * t;
+        if (rows > 128) rows = 128;
+        if (row_lo + rows > total_rows) rows = total_rows - row_lo;
+        if (TF32) {
+          const int rr = q * 32 + lane;
+          if (rr < rows && !(dbg & 4)) {
+            float4* dh = reinterpret_cast<float4*>(reinterpret_cast<float*>(act0) + (row_lo + rr) * 80);
+            float4* dl = reinterpret_cast<float4*>(reinterpret_cast<float*>(act1) + (row_lo + rr) * 80);
+#pragma unroll
+            for (int c4 = 0; c4 < 20; ++c4) {
+              const float4 bb = b2s[c4];
+              const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
+              float h[4], l[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float r = fmaxf(__uint_as_float(v[c4 * 4 + e]) + bv[e], 0.f);
+                h[e] = __uint_as_float(__float_as_uint(r) & 0xFFFFE000u);
+                l[e] = r - h[e];
+              }
+              dh[c4] = make_float4(h[0], h[1], h[2], h[3]);
+              dl[c4] = make_float4(l[0], l[1], l[2], l[3]);
+            }
+          }
+          continue;
+        }
         uint8_t* orow = obuf + (q * 32 + lane) * 160;
 #pragma unroll
         for (int c8 = 0; c8 < 10; ++c8) {
@@ -294,16 +368,13 @@ vt_conv_bf16_kernel(const __grid_constant__ ConvW1 w1c, const float* __restrict_
         fence_proxy_async_smem();
         named_bar_sync(2, 128);
         if (leader) {
-          const long long row_lo = r0 + 128 * t;
-          long long rows = kOutRows - 128 * t;
-          if (rows > 128) rows = 128;
-          if (row_lo + rows > total_rows) rows = total_rows - row_lo;
-          if (rows > 0 && !(dbg & 4)) bulk_s2g(act + row_lo * 80, obuf, (uint32_t)rows * 160);
+          if (rows > 0 && !(dbg & 4))
+            bulk_s2g(reinterpret_cast<__nv_bfloat16*>(act0) + row_lo * 80, obuf, (uint32_t)rows * 160);
           bulk_commit();
         }
       }
     }
-    if (leader) bulk_wait<0>();
+    if (!TF32 && leader) bulk_wait<0>();
   } else {
     // ================= conv1 producers: fp32 FMA -> ReLU -> bf16 -> A operand image.
     // One tape row per thread; a chunk is 16 channels x {I row, Q row}; weights come from the
@@ -338,13 +409,23 @@ vt_conv_bf16_kernel(const __grid_constant__ ConvW1 w1c, const float* __restrict_
 #pragma unroll
       for (int c = 0; c < kChunks; ++c, ++it) {
         // compute the chunk into registers first: nothing here depends on the stage being free
-        uint4 o[kGroups];
+        uint4 o[ConvSmem::kImgs * kGroups];
+        if (!TF32) {
 #pragma unroll
-        for (int hc = 0; hc < kCC / 8; ++hc) {
-          if (dbg & 1) break;
-          const unsigned long long* w = &w1c.v[(c * (kCC / 8) + hc) * 16];
-          o[2 * hc] = conv1_item(xd[0][0], xd[0][1], xd[0][2], w, m);
-          o[2 * hc + 1] = conv1_item(xd[1][0], xd[1][1], xd[1][2], w, m);
+          for (int hc = 0; hc < 2; ++hc) {
+            if (dbg & 1) break;
+            const unsigned long long* w = &w1c.v[(c * 2 + hc) * 16];
+            o[2 * hc] = conv1_item(xd[0][0], xd[0][1], xd[0][2], w, m);
+            o[2 * hc + 1] = conv1_item(xd[1][0], xd[1][1], xd[1][2], w, m);
+          }
+        } else {
+          const unsigned long long* w = &w1c.v[c * 16];       // chunk c = channels 8c .. 8c+7
+#pragma unroll
+          for (int qd = 0; qd < 2; ++qd) {
+            if (dbg & 1) break;
+            conv1_quad(xd[0][0], xd[0][1], xd[0][2], w, qd, m, o[2 * qd], o[kGroups + 2 * qd]);
+            conv1_quad(xd[1][0], xd[1][1], xd[1][2], w, qd, m, o[2 * qd + 1], o[kGroups + 2 * qd + 1]);
+          }
         }
         // publish the PREVIOUS chunk now: its stores were issued a whole chunk of math ago, so the
         // generic->async proxy fence no longer waits on them
@@ -358,7 +439,7 @@ vt_conv_bf16_kernel(const __grid_constant__ ConvW1 w1c, const float* __restrict_
         uint8_t* arow = smem + ConvSmem::a + s * kASlot + row * 16;
         if (!(dbg & 1)) {
 #pragma unroll
-          for (int g = 0; g < kGroups; ++g) *reinterpret_cast<uint4*>(arow + g * kALbo) = o[g];
+          for (int g = 0; g < ConvSmem::kImgs * kGroups; ++g) *reinterpret_cast<uint4*>(arow + g * kALbo) = o[g];
         }
       }
     }
@@ -521,6 +602,154 @@ vt_dense_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
 }
 
 // ------------------------------------------------------------------------------------------
+// dense1 in 3xTF32: h = relu(act W3 + b3) with act = act_hi + act_lo, W3 = W3_hi + W3_lo (fp32 words,
+// tf32 hi/lo split), three kind::tf32 MMAs per K step.  128 frames x 256 outputs per tile, K blocks
+// of 32 values (128-B swizzled rows); 96 KB per stage (A hi/lo 16 KB each, B hi/lo 32 KB each), two
+// stages; accumulators double-buffered in TMEM (2 x 256 columns) so the epilogue overlaps the
+// next tile's mainloop.
+constexpr int kTM = 128;
+constexpr int kTK = 32;
+constexpr int kTStages = 2;
+constexpr int kTKBlocks = kVtFlat / kTK;           // 330
+constexpr int kTABytes = kTM * 128;                // 16 KB
+constexpr int kTBBytes = 256 * 128;                // 32 KB
+constexpr int kTStageBytes = 2 * kTABytes + 2 * kTBBytes;
+constexpr int kDenseT32Threads = 6 * 32;           // TMA, MMA, 4 epilogue warps
+static_assert(kVtFlat % kTK == 0, "K must tile");
+
+struct DenseT32Smem {
+  static constexpr int stages = 0;
+  static constexpr int b3 = kTStages * kTStageBytes;
+  static constexpr int bars = b3 + 1024;
+  static constexpr int nbars = 2 * kTStages + 4;
+  static constexpr int tmem_slot = bars + nbars * 8;
+  static constexpr int total = tmem_slot + 16 + 1024;
+};
+static_assert(DenseT32Smem::total <= 232448, "tf32 dense kernel shared memory exceeds 227 KB");
+
+__global__ void __launch_bounds__(kDenseT32Threads, 1)
+vt_dense_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
+                       const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUtensorMap map_bl,
+                       const float* __restrict__ b3g, float* __restrict__ hbuf, long long n, int num_tiles) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DenseT32Smem::bars);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kTStages;
+  uint64_t* tmem_full = bars + 2 * kTStages;    // [2]
+  uint64_t* tmem_empty = tmem_full + 2;         // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + DenseT32Smem::tmem_slot);
+  const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
+
+  for (int i = tid; i < 256; i += kDenseT32Threads) reinterpret_cast<float*>(smem + DenseT32Smem::b3)[i] = b3g[i];
+  if (tid == 0) {
+    for (int s = 0; s < kTStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full[b], 1);
+      mbar_init(&tmem_empty[b], 4);
+    }
+    fence_barrier_init();
+    prefetch_tensormap(&map_ah);
+    prefetch_tensormap(&map_al);
+    prefetch_tensormap(&map_bh);
+    prefetch_tensormap(&map_bl);
+  }
+  if (warp == 0) tmem_alloc<512>(tmem_slot);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int kb = 0; kb < kTKBlocks; ++kb, ++it) {
+        const uint32_t s = it % kTStages, ph = (it / kTStages) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        if (elect_one()) {
+          uint8_t* st = smem + s * kTStageBytes;
+          mbar_arrive_expect_tx(&full[s], kTStageBytes);
+          tma_load_2d(st, &map_ah, kb * kTK, tile * kTM, &full[s]);
+          tma_load_2d(st + kTABytes, &map_al, kb * kTK, tile * kTM, &full[s]);
+          tma_load_2d(st + 2 * kTABytes, &map_bh, kb * kTK, 0, &full[s]);
+          tma_load_2d(st + 2 * kTABytes + kTBBytes, &map_bl, kb * kTK, 0, &full[s]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = make_idesc_tf32(128, 256);
+    const uint32_t base = smem_u32(smem);
+    constexpr uint32_t hi = smem_desc_hi(1024, 2);
+    uint32_t it = 0, k = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++k) {
+      const uint32_t buf = k & 1;
+      mbar_wait(&tmem_empty[buf], ((k >> 1) & 1) ^ 1);
+      for (int kb = 0; kb < kTKBlocks; ++kb, ++it) {
+        const uint32_t s = it % kTStages, ph = (it / kTStages) & 1;
+        mbar_wait(&full[s], ph);
+        tc_fence_after_sync();
+        if (elect_one()) {
+          const uint32_t st = base + s * kTStageBytes;
+          const uint32_t ah = smem_desc_lo(st, 16), al = smem_desc_lo(st + kTABytes, 16);
+          const uint32_t bh = smem_desc_lo(st + 2 * kTABytes, 16), bl = smem_desc_lo(st + 2 * kTABytes + kTBBytes, 16);
+#pragma unroll
+          for (int ks = 0; ks < kTK / 8; ++ks) {
+            const uint32_t o = (ks * 32) >> 4;
+            mma_tf32_ss(tmem + buf * 256, desc64(al + o, hi), desc64(bh + o, hi), idesc, (kb | ks) != 0);
+            mma_tf32_ss(tmem + buf * 256, desc64(ah + o, hi), desc64(bl + o, hi), idesc, 1);
+            mma_tf32_ss(tmem + buf * 256, desc64(ah + o, hi), desc64(bh + o, hi), idesc, 1);
+          }
+          mma_commit(&empty[s]);
+          if (kb == kTKBlocks - 1) mma_commit(&tmem_full[buf]);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const float* b3s = reinterpret_cast<const float*>(smem + DenseT32Smem::b3);
+    uint32_t k = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++k) {
+      const uint32_t buf = k & 1;
+      mbar_wait(&tmem_full[buf], (k >> 1) & 1);
+      tc_fence_after_sync();
+      const long long row = (long long)tile * kTM + q * 32 + lane;
+      float* dst = hbuf + row * 256;
+#pragma unroll 1
+      for (int cc = 0; cc < 16; ++cc) {
+        uint32_t v0[16];
+        tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + buf * 256 + cc * 16, v0);
+        tmem_ld_wait();
+        if (row < n) {
+#pragma unroll
+          for (int e = 0; e < 16; e += 4) {
+            const int c0 = cc * 16 + e;
+            float4 o;
+            o.x = fmaxf(__uint_as_float(v0[e]) + b3s[c0], 0.f);
+            o.y = fmaxf(__uint_as_float(v0[e + 1]) + b3s[c0 + 1], 0.f);
+            o.z = fmaxf(__uint_as_float(v0[e + 2]) + b3s[c0 + 2], 0.f);
+            o.w = fmaxf(__uint_as_float(v0[e + 3]) + b3s[c0 + 3], 0.f);
+            *reinterpret_cast<float4*>(dst + c0) = o;
+          }
+        }
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+    }
+  }
+
+  __syncwarp();
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
+// ------------------------------------------------------------------------------------------
 // host side
 static uint16_t f2bf(float f) {   // round to nearest even, like cvt.rn.bf16.f32
   uint32_t u;
@@ -542,22 +771,32 @@ static PFN_cuTensorMapEncodeTiled get_encode() {
   return fn;
 }
 
-// [rows][kVtFlat] bf16, K-major: box = 64 K elements (128 B) x 256 rows, 128B swizzle, OOB rows -> 0
-static int make_kmajor_map(CUtensorMap* m, const void* base, uint64_t rows) {
+// [rows][kVtFlat] K-major matrix: box = 128 B of K (64 bf16 / 32 fp32) x box_rows, 128B swizzle, OOB rows -> 0
+static int make_kmajor_map(CUtensorMap* m, const void* base, uint64_t rows, bool f32, uint32_t box_rows) {
   PFN_cuTensorMapEncodeTiled enc = get_encode();
   MDC_REQUIRE(enc != nullptr, MDC_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
   const cuuint64_t dims[2] = {(cuuint64_t)kVtFlat, rows};
-  const cuuint64_t strides[1] = {(cuuint64_t)kVtFlat * 2};
-  const cuuint32_t box[2] = {(cuuint32_t)kDK, (cuuint32_t)kDM};
+  const cuuint64_t strides[1] = {(cuuint64_t)kVtFlat * (f32 ? 4 : 2)};
+  const cuuint32_t box[2] = {(cuuint32_t)(f32 ? kTK : kDK), box_rows};
   const cuuint32_t estr[2] = {1, 1};
-  const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+  const CUresult r = enc(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                         const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   MDC_REQUIRE(r == CUDA_SUCCESS, MDC_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return MDC_OK;
 }
 
-int pack_vt_bf16(mdc_handle_s* h) {
+static void split_tf32(float v, float& hi, float& lo) {   // hi = what the tensor core reads of v; lo exact
+  uint32_t u;
+  memcpy(&u, &v, 4);
+  u &= 0xFFFFE000u;
+  memcpy(&hi, &u, 4);
+  lo = v - hi;
+}
+
+int pack_vt_bf16(mdc_handle_s* h) {      // both tensor-core modes (MDC_MODE_BF16, MDC_MODE_TF32X3)
+  const bool tf32 = h->mode == MDC_MODE_TF32X3;
   if (int e = pack_vt_small(h)) return e;
   // conv1 image: 32 channel groups x {w0[8], w1[8], w2[8], bias[8]} fp32 (Keras (1,3,1,256) = [tap][ch])
   {
@@ -574,73 +813,128 @@ int pack_vt_bf16(mdc_handle_s* h) {
       }
     h->vt_w1_img = img;      // passed by value as a kernel parameter
   }
-  // conv2 image: [chunk][pair rank][tap][group][40 out][8 k] bf16; chunk c = conv1 channels
-  // 16c..16c+15, group g = 2*(channel half) + input row, rank h holds output channels 40h..40h+39
-  // (Keras (2,3,256,80) = [r][j][ch][o])
-  {
-    std::vector<uint16_t> img((size_t)kChunks * 2 * kBSlot / 2);
-    const float* w2 = h->w[MDC_T_CONV2_K].data();
-    for (int c = 0; c < kChunks; ++c)
+  // conv2 image: [chunk][pair rank][hi/lo][tap][group][40 out][16 B]; chunk c = conv1 channels
+  // kCC c .. kCC c + kCC - 1, group g = 2*(channel block) + input row, rank h holds output channels
+  // 40h..40h+39 (Keras (2,3,256,80) = [r][j][ch][o]).  bf16: 8 values per group, one image;
+  // tf32x3: 4 fp32 per group, hi and lo images.
+  const float* w2 = h->w[MDC_T_CONV2_K].data();
+  if (!tf32) {
+    using Cfg = ConvCfg<false>;
+    std::vector<uint16_t> img((size_t)Cfg::kChunks * 2 * Cfg::kBSlot / 2);
+    for (int c = 0; c < Cfg::kChunks; ++c)
       for (int hf = 0; hf < 2; ++hf)
         for (int j = 0; j < 3; ++j)
           for (int g = 0; g < kGroups; ++g)
             for (int oo = 0; oo < kBHalf; ++oo)
               for (int e = 0; e < 8; ++e) {
-                const int r = g & 1, ch = c * kCC + (g >> 1) * 8 + e, o = hf * kBHalf + oo;
-                img[((size_t)(c * 2 + hf) * (kBSlot / 2)) + ((size_t)(j * kGroups + g) * kBHalf + oo) * 8 + e] =
+                const int r = g & 1, ch = c * Cfg::kCC + (g >> 1) * 8 + e, o = hf * kBHalf + oo;
+                img[((size_t)(c * 2 + hf) * (Cfg::kBSlot / 2)) + ((size_t)(j * kGroups + g) * kBHalf + oo) * 8 + e] =
                     f2bf(w2[((size_t)(r * 3 + j) * 256 + ch) * 80 + o]);
               }
     if (int e = h->vt_w2_bf16.reserve(img.size() * 2)) return e;
     MDC_CUDA(cudaMemcpy(h->vt_w2_bf16.ptr, img.data(), img.size() * 2, cudaMemcpyHostToDevice));
+  } else {
+    using Cfg = ConvCfg<true>;
+    std::vector<float> img((size_t)Cfg::kChunks * 2 * Cfg::kBSlot / 4);
+    for (int c = 0; c < Cfg::kChunks; ++c)
+      for (int hf = 0; hf < 2; ++hf)
+        for (int j = 0; j < 3; ++j)
+          for (int g = 0; g < kGroups; ++g)
+            for (int oo = 0; oo < kBHalf; ++oo)
+              for (int e = 0; e < 4; ++e) {
+                const int r = g & 1, ch = c * Cfg::kCC + (g >> 1) * 4 + e, o = hf * kBHalf + oo;
+                float hi, lo;
+                split_tf32(w2[((size_t)(r * 3 + j) * 256 + ch) * 80 + o], hi, lo);
+                const size_t base = (size_t)(c * 2 + hf) * (Cfg::kBSlot / 4) + ((size_t)(j * kGroups + g) * kBHalf + oo) * 4 + e;
+                img[base] = hi;
+                img[base + Cfg::kBImg / 4] = lo;
+              }
+    if (int e = h->vt_w2_bf16.reserve(img.size() * 4)) return e;
+    MDC_CUDA(cudaMemcpy(h->vt_w2_bf16.ptr, img.data(), img.size() * 4, cudaMemcpyHostToDevice));
   }
-  // dense1 image: W3^T [256][10560] bf16 in this library's activation order (pos*80 + ch)
+  // dense1 image: W3^T [256][10560] in this library's activation order (pos*80 + ch);
+  // bf16: one bf16 matrix; tf32x3: fp32 hi matrix followed by the lo matrix
   {
     std::vector<float> w3p;
     vt_permute_w3(h, w3p);
-    std::vector<uint16_t> img((size_t)kVtH * kVtFlat);
-    for (int kx = 0; kx < kVtFlat; ++kx)
-      for (int o = 0; o < kVtH; ++o) img[(size_t)o * kVtFlat + kx] = f2bf(w3p[(size_t)kx * kVtH + o]);
-    if (int e = h->vt_w3_bf16.reserve(img.size() * 2)) return e;
-    MDC_CUDA(cudaMemcpy(h->vt_w3_bf16.ptr, img.data(), img.size() * 2, cudaMemcpyHostToDevice));
-    if (!h->tmap_w3) h->tmap_w3 = aligned_alloc(64, sizeof(CUtensorMap));
-    if (int e = make_kmajor_map(reinterpret_cast<CUtensorMap*>(h->tmap_w3), h->vt_w3_bf16.ptr, kVtH)) return e;
+    const size_t cnt = (size_t)kVtH * kVtFlat;
+    if (!h->tmap_w3) h->tmap_w3 = aligned_alloc(64, 2 * sizeof(CUtensorMap));
+    CUtensorMap* maps = reinterpret_cast<CUtensorMap*>(h->tmap_w3);
+    if (!tf32) {
+      std::vector<uint16_t> img(cnt);
+      for (int kx = 0; kx < kVtFlat; ++kx)
+        for (int o = 0; o < kVtH; ++o) img[(size_t)o * kVtFlat + kx] = f2bf(w3p[(size_t)kx * kVtH + o]);
+      if (int e = h->vt_w3_bf16.reserve(cnt * 2)) return e;
+      MDC_CUDA(cudaMemcpy(h->vt_w3_bf16.ptr, img.data(), cnt * 2, cudaMemcpyHostToDevice));
+      if (int e = make_kmajor_map(&maps[0], h->vt_w3_bf16.ptr, kVtH, false, kDM)) return e;
+    } else {
+      std::vector<float> img(2 * cnt);
+      for (int kx = 0; kx < kVtFlat; ++kx)
+        for (int o = 0; o < kVtH; ++o)
+          split_tf32(w3p[(size_t)kx * kVtH + o], img[(size_t)o * kVtFlat + kx], img[cnt + (size_t)o * kVtFlat + kx]);
+      if (int e = h->vt_w3_bf16.reserve(2 * cnt * 4)) return e;
+      MDC_CUDA(cudaMemcpy(h->vt_w3_bf16.ptr, img.data(), 2 * cnt * 4, cudaMemcpyHostToDevice));
+      const float* base = reinterpret_cast<const float*>(h->vt_w3_bf16.ptr);
+      if (int e = make_kmajor_map(&maps[0], base, kVtH, true, 256)) return e;
+      if (int e = make_kmajor_map(&maps[1], base + cnt, kVtH, true, 256)) return e;
+    }
   }
-  MDC_CUDA(cudaFuncSetAttribute(vt_conv_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvSmem::total));
+  MDC_CUDA(cudaFuncSetAttribute(vt_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<false>::total));
+  MDC_CUDA(cudaFuncSetAttribute(vt_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<true>::total));
   MDC_CUDA(cudaFuncSetAttribute(vt_dense_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DenseSmem::total));
+  MDC_CUDA(cudaFuncSetAttribute(vt_dense_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DenseT32Smem::total));
   return MDC_OK;
 }
 
 int launch_vt_bf16(mdc_handle_s* h, const float* x, int64_t n, float* probs, float* dense,
                    int32_t* cls, unsigned long long* hist, cudaStream_t stream) {
-  constexpr int64_t CH = 65536;     // frames per pass: act = 1.38 GB, h = 64 MB of workspace
+  const bool tf32 = h->mode == MDC_MODE_TF32X3;
+  // frames per pass.  bf16: act = 21 KB/frame -> 1.38 GB; tf32x3: hi + lo fp32 = 84 KB/frame, and
+  // 148 x 128 frames is exactly one wave of dense tiles -> 1.6 GB
+  const int64_t CH = tf32 ? (int64_t)h->num_sms * kTM : 65536;
   const int64_t cap = n < CH ? n : CH;
   if (n == 0) return MDC_OK;
-  if (int e = h->ws_act.reserve((size_t)cap * kVtFlat * 2)) return e;
+  const size_t act_elems = (size_t)cap * kVtFlat;
+  if (int e = h->ws_act.reserve(tf32 ? act_elems * 8 : act_elems * 2)) return e;
   if (int e = h->ws_h.reserve((size_t)cap * kVtH * 4)) return e;
-  __nv_bfloat16* act = reinterpret_cast<__nv_bfloat16*>(h->ws_act.ptr);
+  void* act0 = h->ws_act.ptr;
+  void* act1 = tf32 ? reinterpret_cast<float*>(h->ws_act.ptr) + act_elems : nullptr;
   float* hb = reinterpret_cast<float*>(h->ws_h.ptr);
   ConvW1 w1c;
   static_assert(sizeof(ConvW1) == 32 * 32 * sizeof(float), "conv1 image size");
   memcpy(&w1c, h->vt_w1_img.data(), sizeof(w1c));
   static const int dbg = getenv("MDC_VT_DEBUG") ? atoi(getenv("MDC_VT_DEBUG")) : 0;   // timing experiments
+  const CUtensorMap* wmaps = reinterpret_cast<const CUtensorMap*>(h->tmap_w3);
   for (int64_t s = 0; s < n; s += CH) {
     const int64_t m = (n - s) < CH ? (n - s) : CH;
     const long long num_st = (m * 132 + kOutRows - 1) / kOutRows;
     const long long pairs_needed = (num_st + 1) / 2, pairs_max = h->num_sms / 2;
     const unsigned grid_c = 2u * (unsigned)(pairs_needed < pairs_max ? pairs_needed : pairs_max);
+    const float* b2 = reinterpret_cast<const float*>(h->vt_b2.ptr);
+    const uint8_t* w2 = reinterpret_cast<const uint8_t*>(h->vt_w2_bf16.ptr);
     prof_begin(h, stream);
-    vt_conv_bf16_kernel<<<grid_c, kConvThreads, ConvSmem::total, stream>>>(
-        w1c, x + s * 256, m, reinterpret_cast<const float*>(h->vt_b2.ptr),
-        reinterpret_cast<const uint8_t*>(h->vt_w2_bf16.ptr), act, num_st, dbg);
+    if (tf32)
+      vt_conv_kernel<true><<<grid_c, kConvThreads, ConvCfg<true>::total, stream>>>(w1c, x + s * 256, m, b2, w2, act0, act1, num_st, dbg);
+    else
+      vt_conv_kernel<false><<<grid_c, kConvThreads, ConvCfg<false>::total, stream>>>(w1c, x + s * 256, m, b2, w2, act0, act1, num_st, dbg);
     prof_end(h, stream);
     MDC_CUDA(cudaGetLastError());
-    CUtensorMap map_a;
-    if (int e = make_kmajor_map(&map_a, act, (uint64_t)m)) return e;
-    const int tiles = (int)((m + kDM - 1) / kDM);
-    const unsigned grid_d = (unsigned)(tiles < h->num_sms ? tiles : h->num_sms);
-    vt_dense_bf16_kernel<<<grid_d, kDenseThreads, DenseSmem::total, stream>>>(
-        map_a, *reinterpret_cast<const CUtensorMap*>(h->tmap_w3), reinterpret_cast<const float*>(h->vt_b3.ptr), hb, m,
-        tiles);
+    const float* b3 = reinterpret_cast<const float*>(h->vt_b3.ptr);
+    if (!tf32) {
+      CUtensorMap map_a;
+      if (int e = make_kmajor_map(&map_a, act0, (uint64_t)m, false, kDM)) return e;
+      const int tiles = (int)((m + kDM - 1) / kDM);
+      const unsigned grid_d = (unsigned)(tiles < h->num_sms ? tiles : h->num_sms);
+      vt_dense_bf16_kernel<<<grid_d, kDenseThreads, DenseSmem::total, stream>>>(map_a, wmaps[0], b3, hb, m, tiles);
+    } else {
+      CUtensorMap map_ah, map_al;
+      if (int e = make_kmajor_map(&map_ah, act0, (uint64_t)m, true, kTM)) return e;
+      if (int e = make_kmajor_map(&map_al, act1, (uint64_t)m, true, kTM)) return e;
+      const int tiles = (int)((m + kTM - 1) / kTM);
+      const unsigned grid_d = (unsigned)(tiles < h->num_sms ? tiles : h->num_sms);
+      vt_dense_tf32x3_kernel<<<grid_d, kDenseT32Threads, DenseT32Smem::total, stream>>>(map_ah, map_al, wmaps[0], wmaps[1],
+                                                                                         b3, hb, m, tiles);
+    }
     h->launches += 2;
     MDC_CUDA(cudaGetLastError());
     if (int e = launch_vt_head(h, hb, m, probs ? probs + s * h->C : nullptr, dense ? dense + s * h->C : nullptr,

@@ -30,7 +30,7 @@ from .h5lite import H5File
 
 __all__ = ["CNN2Model", "tiny_cnn2", "vt_cnn2", "load_model", "read_keras_weights"]
 
-_MODES = {"fp32": _lib.MODE_FP32, "bf16": _lib.MODE_BF16}
+_MODES = {"fp32": _lib.MODE_FP32, "bf16": _lib.MODE_BF16, "tf32x3": _lib.MODE_TF32X3}
 
 
 def _is_torch(x) -> bool:

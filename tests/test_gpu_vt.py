@@ -50,6 +50,25 @@ def test_fp32_channels_first_flatten(vt):
     assert np.max(np.abs(z - ref["logits"][:64]) / scale) < 1e-5
 
 
+def test_tf32x3_mode_within_1e5(vt):
+    """3xTF32 on the tensor cores: every fp32 operand split into tf32 hi + lo, three MMAs per product.
+    Same bar as the fp32 CUDA-core mode: logits within 1e-5 of the largest logit of the fp64 oracle."""
+    from modulationdetectioncnn_b200.model import vt_cnn2
+    w, x, ref = vt
+    m = vt_cnn2(11, mode="tf32x3")
+    m.set_weights(_wlist(w))
+    z = m.predict(x, output="dense")
+    scale = np.abs(ref["logits"]).max(axis=-1, keepdims=True)
+    err = np.abs(z - ref["logits"]) / scale
+    assert err.max() < 1e-5, err.max()
+    p = m.predict(x)
+    np.testing.assert_allclose(p, ref["softmax"], rtol=1e-4, atol=1e-7)
+    assert np.array_equal(m.predict_classes(x), ref["logits"].argmax(-1))
+    for n in (1, 3, 129):
+        assert np.array_equal(m.predict(x[:n], output="dense"), z[:n]), n
+    assert m.class_histogram(x).sum() == x.shape[0]
+
+
 def test_bf16_mode_tolerance(vt):
     """bf16 operands, fp32 accumulate: logits within 2e-2 of the largest logit; argmax agrees
     wherever the oracle's top-2 margin exceeds that error."""
