@@ -40,31 +40,42 @@ void vt_permute_w3(const mdc_handle_s* h, std::vector<float>& out);
 // chunk; one M = 256 MMA issued by the pair's leader covers a 128-row tile of each CTA, so the
 // B operand is fetched from shared memory once per pair (measured: 45 cycles per MMA against 52
 // for the single-CTA M = 128 x N = 80 shape, tools/umma_rate.cu / tools/umma2_probe.cu).
-constexpr int kNT = 3;                    // accumulator tiles (128 rows x 80 cols) per super-tile
-constexpr int kTapeRows = 128 * kNT;      // 384 tape rows staged per super-tile
-constexpr int kOutRows = kTapeRows - 2;   // 382 conv2 rows produced per super-tile (2-row halo)
 constexpr int kGroups = 4;                // 16-B K groups per chunk image: g = 2 * (channel block) + input row
-constexpr int kALbo = kTapeRows * 16;     // bytes between K groups of the A image
 constexpr int kBHalf = 40;                // W2 output channels held by each CTA of the pair
 constexpr int kBLbo = kBHalf * 16;        // bytes between K groups of the B image
 constexpr int kXFrames = 4;               // frames a super-tile's tape rows can touch
 constexpr int kOutTile = 128 * 160;       // one 128 x 80 bf16 output tile
 constexpr int kProdWarp0 = 6;
-constexpr int kProdWarps = kTapeRows / 32;             // 12: one tape row per producer thread
-constexpr int kConvThreads = (kProdWarp0 + kProdWarps) * 32;   // TMA, MMA, 4 epilogue, 12 producers
-constexpr int kAccCols = kNT * 80;        // TMEM columns per accumulator buffer (two buffers)
 
 // A chunk is kCC conv1 channels x {I row, Q row} = two UMMA K steps of two 16-B groups:
 //   bf16:   16 channels, 8 per group, one image        (K step = 16 values)
 //   tf32x3:  8 channels, 4 per group, hi and lo images  (K step =  8 values)
+//
+// 3xTF32 accumulation.  tcgen05.mma rounds every accumulate TOWARD ZERO (tools/umma_acc_probe.cu: 1 + 0.75 ulp
+// stays 1), so a chain of n MMAs into one accumulator comes out low by about n x 1.5e-8 relative (measured
+// -8.8e-6 for the 576-MMA conv2 chain, -6e-5 for the 3,960-MMA dense1 chain).  The tf32x3 conv kernel
+// therefore works on ONE 128-row tile per super-tile and spreads its MMAs over six TMEM accumulators:
+// accumulator 0 takes the two small cross terms (lo*hi, hi*lo) of every K step, accumulators 1..5 take the
+// hi*hi terms of chunks c = a - 1 (mod 5) - at most 42 truncating adds each - and the epilogue adds the six
+// in fp32 round-to-nearest.  The accumulators are single-buffered (6 x 80 = 480 of 512 columns): the MMA
+// warp waits while the epilogue reads them (about 4 % of a tile's 576 MMAs).
 template <bool TF32>
 struct ConvCfg {
+  static constexpr int kNT = TF32 ? 1 : 3;                 // accumulator tiles (128 rows x 80 cols) per super-tile
+  static constexpr int kTapeRows = 128 * kNT;              // tape rows staged per super-tile
+  static constexpr int kOutRows = kTapeRows - 2;           // conv2 rows produced per super-tile (2-row halo)
+  static constexpr int kALbo = kTapeRows * 16;             // bytes between K groups of the A image
+  static constexpr int kProdWarps = kTapeRows / 32;        // one tape row per producer thread
+  static constexpr int kThreads = (kProdWarp0 + kProdWarps) * 32;   // TMA, MMA, 4 epilogue, producers
+  static constexpr int kAccBufs = TF32 ? 1 : 2;            // accumulator buffers in TMEM
+  static constexpr int kAccSplit = TF32 ? 6 : 1;           // accumulators per tile (see above)
+  static constexpr int kAccCols = kNT * kAccSplit * 80;    // TMEM columns per buffer
   static constexpr int kCC = TF32 ? 8 : 16;
   static constexpr int kPerGroup = TF32 ? 4 : 8;
   static constexpr int kImgs = TF32 ? 2 : 1;
   static constexpr int kChunks = 256 / kCC;
-  static constexpr int kStages = TF32 ? 3 : 5;
-  static constexpr int kAImg = kGroups * kALbo;            // 24,576
+  static constexpr int kStages = 5;
+  static constexpr int kAImg = kGroups * kALbo;            // bf16 24,576; tf32 8,192
   static constexpr int kASlot = kImgs * kAImg;
   static constexpr int kBImg = 3 * kGroups * kBLbo;        // 7,680: [tap][group][40][16 B]
   static constexpr int kBSlot = kImgs * kBImg;
@@ -79,9 +90,9 @@ struct ConvCfg {
   static constexpr int nbars = 2 * kStages + 4 + 4;
   static constexpr int tmem_slot = bars + nbars * 8;
   static constexpr int total = tmem_slot + 16;
+  static_assert(kAccBufs * kAccCols <= 512, "accumulators exceed TMEM");
 };
 static_assert(ConvCfg<false>::total <= 232448 && ConvCfg<true>::total <= 232448, "conv kernel shared memory exceeds 227 KB");
-static_assert(2 * kAccCols <= 512, "accumulators exceed TMEM");
 
 __device__ __forceinline__ uint64_t pack_dup(float v) {
   uint64_t d;
@@ -142,13 +153,17 @@ __device__ __forceinline__ void conv1_quad(uint64_t x0, uint64_t x1, uint64_t x2
 
 // act0/act1: bf16 mode -> act0 = bf16 [rows][80]; tf32x3 mode -> act0 = hi, act1 = lo, fp32 [rows][80]
 template <bool TF32>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ConvCfg<TF32>::kThreads, 1)
 vt_conv_kernel(const __grid_constant__ ConvW1 w1c, const float* __restrict__ x, long long n,
                const float* __restrict__ b2g, const uint8_t* __restrict__ w2img,
                void* __restrict__ act0, void* __restrict__ act1, long long num_st, int dbg_rt) {
   using ConvSmem = ConvCfg<TF32>;
   constexpr int kStages = ConvSmem::kStages, kChunks = ConvSmem::kChunks;
   constexpr int kASlot = ConvSmem::kASlot, kBSlot = ConvSmem::kBSlot, kAImg = ConvSmem::kAImg, kBImg = ConvSmem::kBImg;
+  constexpr int kNT = ConvSmem::kNT, kTapeRows = ConvSmem::kTapeRows, kOutRows = ConvSmem::kOutRows, kALbo = ConvSmem::kALbo;
+  constexpr int kProdWarps = ConvSmem::kProdWarps, kConvThreads = ConvSmem::kThreads, kAccCols = ConvSmem::kAccCols;
+  constexpr int kAccBufs = ConvSmem::kAccBufs;
+  (void)kTapeRows;
   // role-ablation flags for timing experiments (build with -DMDC_VT_ABLATE, set MDC_VT_DEBUG; the
   // results are garbage): 1 = producers skip conv1 math and stores, 2 = MMA warp skips the MMAs,
   // 4 = epilogue skips TMEM loads / math / stores.  Compiled out of the product build.
@@ -236,10 +251,11 @@ vt_conv_kernel(const __grid_constant__ ConvW1 w1c, const float* __restrict__ x, 
       const uint32_t a_base = smem_u32(smem + ConvSmem::a), b_base = smem_u32(smem + ConvSmem::b);
       constexpr uint32_t hi = smem_desc_hi(128, 0);
       for (long long base = st_first; base < num_st; base += st_step, ++k) {
-        const uint32_t buf = k & 1;
+        const uint32_t buf = k % kAccBufs, use = k / kAccBufs;
         const uint32_t acc = tmem + buf * kAccCols;
-        mbar_wait(&tmem_empty[buf], ((k >> 1) & 1) ^ 1);     // both epilogues drained this buffer
-        mbar_wait_cluster(&tmem_empty[buf], ((k >> 1) & 1) ^ 1);
+        mbar_wait(&tmem_empty[buf], (use & 1) ^ 1);          // both epilogues drained this buffer
+        mbar_wait_cluster(&tmem_empty[buf], (use & 1) ^ 1);
+        tc_fence_after_sync();
         for (int c = 0; c < kChunks; ++c, ++it) {
           const uint32_t s = it % kStages, ph = (it / kStages) & 1;
           mbar_wait(&full[s], ph);               // cheap cta-scope spin ...
@@ -248,6 +264,8 @@ vt_conv_kernel(const __grid_constant__ ConvW1 w1c, const float* __restrict__ x, 
           if (elect_one()) {
             const uint32_t a_lo = smem_desc_lo(a_base + s * kASlot, kALbo);
             const uint32_t b_lo = smem_desc_lo(b_base + s * kBSlot, kBLbo);
+            // tf32x3: hi*hi terms of chunk c go to accumulator 1 + c % 5, the cross terms to accumulator 0
+            const uint32_t acc_hh = acc + (1 + c % 5) * 80;
 #pragma unroll
             for (int t = 0; t < kNT; ++t) {
               if (dbg & 2) continue;
@@ -261,12 +279,11 @@ vt_conv_kernel(const __grid_constant__ ConvW1 w1c, const float* __restrict__ x, 
                     mma_bf16_ss_pair(acc + t * 80, desc64(a_lo + ao, hi), desc64(b_lo + bo, hi), idesc,
                                      (c | ks | j) != 0);
                   } else {
-                    // small cross terms first, then hi*hi
                     constexpr uint32_t al = kAImg >> 4, bl = kBImg >> 4;   // offsets of the lo images
-                    mma_tf32_ss_pair(acc + t * 80, desc64(a_lo + ao + al, hi), desc64(b_lo + bo, hi), idesc,
-                                     (c | ks | j) != 0);
-                    mma_tf32_ss_pair(acc + t * 80, desc64(a_lo + ao, hi), desc64(b_lo + bo + bl, hi), idesc, 1);
-                    mma_tf32_ss_pair(acc + t * 80, desc64(a_lo + ao, hi), desc64(b_lo + bo, hi), idesc, 1);
+                    mma_tf32_ss_pair(acc, desc64(a_lo + ao + al, hi), desc64(b_lo + bo, hi), idesc, (c | ks | j) != 0);
+                    mma_tf32_ss_pair(acc, desc64(a_lo + ao, hi), desc64(b_lo + bo + bl, hi), idesc, 1);
+                    mma_tf32_ss_pair(acc_hh, desc64(a_lo + ao, hi), desc64(b_lo + bo, hi), idesc,
+                                     (c >= 5) || (ks | j) != 0);
                   }
                 }
               }
@@ -296,8 +313,8 @@ vt_conv_kernel(const __grid_constant__ ConvW1 w1c, const float* __restrict__ x, 
     uint32_t k = 0, tile_ctr = 0;
     for (long long base = st_first; base < num_st; base += st_step, ++k) {
       const long long r0 = (base + rank) * kOutRows;
-      const uint32_t buf = k & 1;
-      mbar_wait(&tmem_full[buf], (k >> 1) & 1);
+      const uint32_t buf = k % kAccBufs, use = k / kAccBufs;
+      mbar_wait(&tmem_full[buf], use & 1);
       tc_fence_after_sync();
 #pragma unroll 1
       for (int t = 0; t < kNT; ++t, ++tile_ctr) {
@@ -307,16 +324,33 @@ vt_conv_kernel(const __grid_constant__ ConvW1 w1c, const float* __restrict__ x, 
           named_bar_sync(1, 128);
         }
         uint32_t v[80];
-        if (!(dbg & 4)) {
+        const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + buf * kAccCols;
+        if (dbg & 4) {
+#pragma unroll
+          for (int i = 0; i < 80; ++i) v[i] = 0;
+        } else if (!TF32) {
 #pragma unroll
           for (int cc = 0; cc < 5; ++cc) {
             uint32_t(&vv)[16] = *reinterpret_cast<uint32_t(*)[16]>(&v[cc * 16]);
-            tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + buf * kAccCols + t * 80 + cc * 16, vv);
+            tmem_ld16(tbase + t * 80 + cc * 16, vv);
           }
           tmem_ld_wait();
         } else {
+          // six partial accumulators -> one fp32 sum, round-to-nearest: ((h1 + h2) + (h3 + h4)) + h5, then the
+          // small cross-term sum
 #pragma unroll
-          for (int i = 0; i < 80; ++i) v[i] = 0;
+          for (int cc = 0; cc < 5; ++cc) {
+            uint32_t p[6][16];
+#pragma unroll
+            for (int a = 0; a < 6; ++a) tmem_ld16(tbase + a * 80 + cc * 16, p[a]);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              const float hh = ((__uint_as_float(p[1][e]) + __uint_as_float(p[2][e])) +
+                                (__uint_as_float(p[3][e]) + __uint_as_float(p[4][e]))) + __uint_as_float(p[5][e]);
+              v[cc * 16 + e] = __float_as_uint(hh + __uint_as_float(p[0][e]));
+            }
+          }
         }
         if (t == kNT - 1) {                       // whole buffer read: hand it back to the MMA warp
           tc_fence_before_sync();
@@ -605,8 +639,12 @@ vt_dense_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
 // dense1 in 3xTF32: h = relu(act W3 + b3) with act = act_hi + act_lo, W3 = W3_hi + W3_lo (fp32 words,
 // tf32 hi/lo split), three kind::tf32 MMAs per K step.  128 frames x 256 outputs per tile, K blocks
 // of 32 values (128-B swizzled rows); 96 KB per stage (A hi/lo 16 KB each, B hi/lo 32 KB each), two
-// stages; accumulators double-buffered in TMEM (2 x 256 columns) so the epilogue overlaps the
-// next tile's mainloop.
+// stages.
+//
+// K = 10,560 would be a chain of 3,960 truncating accumulates (see ConvCfg), so the tensor core only
+// ever sums ONE K block: every block starts a fresh accumulator (12 MMAs) in one of two TMEM buffers,
+// and eight epilogue warps fold the finished buffer into fp32 master sums held in registers (128 per
+// thread, round-to-nearest FADD) while the MMAs of the next block fill the other buffer.
 constexpr int kTM = 128;
 constexpr int kTK = 32;
 constexpr int kTStages = 2;
@@ -614,7 +652,8 @@ constexpr int kTKBlocks = kVtFlat / kTK;           // 330
 constexpr int kTABytes = kTM * 128;                // 16 KB
 constexpr int kTBBytes = 256 * 128;                // 32 KB
 constexpr int kTStageBytes = 2 * kTABytes + 2 * kTBBytes;
-constexpr int kDenseT32Threads = 6 * 32;           // TMA, MMA, 4 epilogue warps
+constexpr int kTEpiWarps = 8;                      // (TMEM lane quarter) x (column half)
+constexpr int kDenseT32Threads = (2 + kTEpiWarps) * 32;   // TMA, MMA, 8 epilogue warps
 static_assert(kVtFlat % kTK == 0, "K must tile");
 
 struct DenseT32Smem {
@@ -636,8 +675,8 @@ vt_dense_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DenseT32Smem::bars);
   uint64_t* full = bars;
   uint64_t* empty = bars + kTStages;
-  uint64_t* tmem_full = bars + 2 * kTStages;    // [2]
-  uint64_t* tmem_empty = tmem_full + 2;         // [2]
+  uint64_t* acc_full = bars + 2 * kTStages;     // [2] one K block summed into this TMEM buffer
+  uint64_t* acc_empty = acc_full + 2;           // [2] the epilogue warps have folded it into their registers
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + DenseT32Smem::tmem_slot);
   const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
 
@@ -648,8 +687,8 @@ vt_dense_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_
       mbar_init(&empty[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(&tmem_full[b], 1);
-      mbar_init(&tmem_empty[b], 4);
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], kTEpiWarps);
     }
     fence_barrier_init();
     prefetch_tensormap(&map_ah);
@@ -684,12 +723,12 @@ vt_dense_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_
     const uint32_t idesc = make_idesc_tf32(128, 256);
     const uint32_t base = smem_u32(smem);
     constexpr uint32_t hi = smem_desc_hi(1024, 2);
-    uint32_t it = 0, k = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++k) {
-      const uint32_t buf = k & 1;
-      mbar_wait(&tmem_empty[buf], ((k >> 1) & 1) ^ 1);
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       for (int kb = 0; kb < kTKBlocks; ++kb, ++it) {
         const uint32_t s = it % kTStages, ph = (it / kTStages) & 1;
+        const uint32_t buf = it & 1;
+        mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);
         mbar_wait(&full[s], ph);
         tc_fence_after_sync();
         if (elect_one()) {
@@ -699,47 +738,59 @@ vt_dense_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_
 #pragma unroll
           for (int ks = 0; ks < kTK / 8; ++ks) {
             const uint32_t o = (ks * 32) >> 4;
-            mma_tf32_ss(tmem + buf * 256, desc64(al + o, hi), desc64(bh + o, hi), idesc, (kb | ks) != 0);
+            mma_tf32_ss(tmem + buf * 256, desc64(al + o, hi), desc64(bh + o, hi), idesc, ks != 0);
             mma_tf32_ss(tmem + buf * 256, desc64(ah + o, hi), desc64(bl + o, hi), idesc, 1);
             mma_tf32_ss(tmem + buf * 256, desc64(ah + o, hi), desc64(bh + o, hi), idesc, 1);
           }
           mma_commit(&empty[s]);
-          if (kb == kTKBlocks - 1) mma_commit(&tmem_full[buf]);
+          mma_commit(&acc_full[buf]);
         }
         __syncwarp();
       }
     }
   } else {
-    const int q = warp & 3;
-    const float* b3s = reinterpret_cast<const float*>(smem + DenseT32Smem::b3);
-    uint32_t k = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++k) {
-      const uint32_t buf = k & 1;
-      mbar_wait(&tmem_full[buf], (k >> 1) & 1);
-      tc_fence_after_sync();
-      const long long row = (long long)tile * kTM + q * 32 + lane;
-      float* dst = hbuf + row * 256;
-#pragma unroll 1
-      for (int cc = 0; cc < 16; ++cc) {
-        uint32_t v0[16];
-        tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + buf * 256 + cc * 16, v0);
-        tmem_ld_wait();
-        if (row < n) {
+    const int q = warp & 3, half = (warp - 2) >> 2;          // TMEM lane quarter, column half
+    const float* b3s = reinterpret_cast<const float*>(smem + DenseT32Smem::b3) + half * 128;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      float acc[128];
 #pragma unroll
-          for (int e = 0; e < 16; e += 4) {
-            const int c0 = cc * 16 + e;
-            float4 o;
-            o.x = fmaxf(__uint_as_float(v0[e]) + b3s[c0], 0.f);
-            o.y = fmaxf(__uint_as_float(v0[e + 1]) + b3s[c0 + 1], 0.f);
-            o.z = fmaxf(__uint_as_float(v0[e + 2]) + b3s[c0 + 2], 0.f);
-            o.w = fmaxf(__uint_as_float(v0[e + 3]) + b3s[c0 + 3], 0.f);
-            *reinterpret_cast<float4*>(dst + c0) = o;
+      for (int i = 0; i < 128; ++i) acc[i] = 0.f;
+#pragma unroll 1
+      for (int kb = 0; kb < kTKBlocks; ++kb, ++it) {
+        const uint32_t buf = it & 1;
+        mbar_wait(&acc_full[buf], (it >> 1) & 1);
+        tc_fence_after_sync();
+        const uint32_t tb = tmem + ((uint32_t)(q * 32) << 16) + buf * 256 + half * 128;
+#pragma unroll
+        for (int g = 0; g < 4; g += 2) {
+          uint32_t v0[32], v1[32];
+          tmem_ld32(tb + g * 32, v0);
+          tmem_ld32(tb + g * 32 + 32, v1);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            acc[g * 32 + e] += __uint_as_float(v0[e]);
+            acc[g * 32 + 32 + e] += __uint_as_float(v1[e]);
           }
         }
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[buf]);
       }
-      tc_fence_before_sync();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+      const long long row = (long long)tile * kTM + q * 32 + lane;
+      if (row < n) {
+        float* dst = hbuf + row * 256 + half * 128;
+#pragma unroll
+        for (int e = 0; e < 128; e += 4) {
+          float4 o;
+          o.x = fmaxf(acc[e] + b3s[e], 0.f);
+          o.y = fmaxf(acc[e + 1] + b3s[e + 1], 0.f);
+          o.z = fmaxf(acc[e + 2] + b3s[e + 2], 0.f);
+          o.w = fmaxf(acc[e + 3] + b3s[e + 3], 0.f);
+          *reinterpret_cast<float4*>(dst + e) = o;
+        }
+      }
     }
   }
 
@@ -907,16 +958,17 @@ int launch_vt_bf16(mdc_handle_s* h, const float* x, int64_t n, float* probs, flo
   const CUtensorMap* wmaps = reinterpret_cast<const CUtensorMap*>(h->tmap_w3);
   for (int64_t s = 0; s < n; s += CH) {
     const int64_t m = (n - s) < CH ? (n - s) : CH;
-    const long long num_st = (m * 132 + kOutRows - 1) / kOutRows;
+    const long long out_rows = tf32 ? ConvCfg<true>::kOutRows : ConvCfg<false>::kOutRows;
+    const long long num_st = (m * 132 + out_rows - 1) / out_rows;
     const long long pairs_needed = (num_st + 1) / 2, pairs_max = h->num_sms / 2;
     const unsigned grid_c = 2u * (unsigned)(pairs_needed < pairs_max ? pairs_needed : pairs_max);
     const float* b2 = reinterpret_cast<const float*>(h->vt_b2.ptr);
     const uint8_t* w2 = reinterpret_cast<const uint8_t*>(h->vt_w2_bf16.ptr);
     prof_begin(h, stream);
     if (tf32)
-      vt_conv_kernel<true><<<grid_c, kConvThreads, ConvCfg<true>::total, stream>>>(w1c, x + s * 256, m, b2, w2, act0, act1, num_st, dbg);
+      vt_conv_kernel<true><<<grid_c, ConvCfg<true>::kThreads, ConvCfg<true>::total, stream>>>(w1c, x + s * 256, m, b2, w2, act0, act1, num_st, dbg);
     else
-      vt_conv_kernel<false><<<grid_c, kConvThreads, ConvCfg<false>::total, stream>>>(w1c, x + s * 256, m, b2, w2, act0, act1, num_st, dbg);
+      vt_conv_kernel<false><<<grid_c, ConvCfg<false>::kThreads, ConvCfg<false>::total, stream>>>(w1c, x + s * 256, m, b2, w2, act0, act1, num_st, dbg);
     prof_end(h, stream);
     MDC_CUDA(cudaGetLastError());
     const float* b3 = reinterpret_cast<const float*>(h->vt_b3.ptr);
