@@ -54,6 +54,7 @@ struct HostPipe {
   static constexpr int kSlots = 3;
   cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr;
   cudaEvent_t e_h2d[kSlots] = {}, e_comp[kSlots] = {}, e_d2h[kSlots] = {};
+  cudaEvent_t e_pass[2] = {}, e_pass_d2h[2] = {};      // tensor-core VT path: per-pass output buffers
   DeviceBuffer x[kSlots], o0[kSlots], o1[kSlots], o2[kSlots];
   DeviceBuffer hist;
   int init() {
@@ -66,6 +67,10 @@ struct HostPipe {
       MDC_CUDA(cudaEventCreateWithFlags(&e_comp[i], cudaEventDisableTiming));
       MDC_CUDA(cudaEventCreateWithFlags(&e_d2h[i], cudaEventDisableTiming));
     }
+    for (int i = 0; i < 2; ++i) {
+      MDC_CUDA(cudaEventCreateWithFlags(&e_pass[i], cudaEventDisableTiming));
+      MDC_CUDA(cudaEventCreateWithFlags(&e_pass_d2h[i], cudaEventDisableTiming));
+    }
     return hist.reserve(kMaxClasses * kMaxClasses * sizeof(unsigned long long));
   }
   void destroy() {
@@ -75,6 +80,7 @@ struct HostPipe {
       cudaEventDestroy(e_h2d[i]); cudaEventDestroy(e_comp[i]); cudaEventDestroy(e_d2h[i]);
       x[i].release(); o0[i].release(); o1[i].release(); o2[i].release();
     }
+    for (int i = 0; i < 2; ++i) { cudaEventDestroy(e_pass[i]); cudaEventDestroy(e_pass_d2h[i]); }
     hist.release();
     cudaStreamDestroy(s_h2d); cudaStreamDestroy(s_comp); cudaStreamDestroy(s_d2h);
     s_h2d = nullptr;
@@ -189,6 +195,65 @@ static int run_host_pipeline(mdc_handle_s* h, const In* x, int64_t n, O0* o0, O1
   return MDC_OK;
 }
 
+
+// Tensor-core VT-CNN2 (bf16 / 3xTF32) from host buffers.  The frames travel in small chunks (8 MiB) so the
+// first convolution starts early and every later copy hides under the previous chunk's convolution; dense1
+// and the head run ONCE per pass over all the activations (a dense tile is 256 frames per SM: per-chunk
+// launches would leave most SMs idle), and the pass's results are copied back under the next pass.
+static int run_vt_host_pipeline(mdc_handle_s* h, const float* x, int64_t n, float* probs, float* dense, int32_t* cls,
+                                unsigned long long* hist) {
+  if (!h->pipe) h->pipe = new HostPipe();
+  HostPipe& P = *h->pipe;
+  if (int e = P.init()) return e;
+  const int C = h->C;
+  constexpr int S = HostPipe::kSlots;
+  const int64_t pass = vt_pass_frames(h);
+  const int64_t chunk = h->mode == MDC_MODE_TF32X3 ? pass : 8192;
+  const int64_t cap = n < pass ? n : pass;
+  if (int e = vt_reserve(h, cap)) return e;
+  if (hist) MDC_CUDA(cudaMemsetAsync(P.hist.ptr, 0, C * sizeof(unsigned long long), P.s_comp));
+  for (int k = 0; k < S; ++k)
+    if (int e = P.x[k].reserve((size_t)(cap < chunk ? cap : chunk) * kFrameElems * sizeof(float))) return e;
+  for (int b = 0; b < 2; ++b) {
+    if (probs) if (int e = P.o0[b].reserve((size_t)cap * C * sizeof(float))) return e;
+    if (dense) if (int e = P.o1[b].reserve((size_t)cap * C * sizeof(float))) return e;
+    if (cls) if (int e = P.o2[b].reserve((size_t)cap * sizeof(int32_t))) return e;
+  }
+  int64_t i = 0, pi = 0;
+  for (int64_t p0 = 0; p0 < n; p0 += pass, ++pi) {
+    const int64_t pm = (n - p0) < pass ? (n - p0) : pass;
+    const int ob = (int)(pi & 1);
+    for (int64_t c0 = 0; c0 < pm; c0 += chunk, ++i) {
+      const int k = (int)(i % S);
+      const int64_t m = (pm - c0) < chunk ? (pm - c0) : chunk;
+      if (i >= S) MDC_CUDA(cudaStreamWaitEvent(P.s_h2d, P.e_comp[k], 0));
+      MDC_CUDA(cudaMemcpyAsync(P.x[k].ptr, x + (p0 + c0) * kFrameElems, (size_t)m * kFrameElems * sizeof(float),
+                               cudaMemcpyHostToDevice, P.s_h2d));
+      MDC_CUDA(cudaEventRecord(P.e_h2d[k], P.s_h2d));
+      MDC_CUDA(cudaStreamWaitEvent(P.s_comp, P.e_h2d[k], 0));
+      if (int e = launch_vt_conv(h, (const float*)P.x[k].ptr, m, c0, P.s_comp)) return e;
+      MDC_CUDA(cudaEventRecord(P.e_comp[k], P.s_comp));
+    }
+    if (pi >= 2) MDC_CUDA(cudaStreamWaitEvent(P.s_comp, P.e_pass_d2h[ob], 0));
+    if (int e = launch_vt_dense_head(h, pm, probs ? (float*)P.o0[ob].ptr : nullptr, dense ? (float*)P.o1[ob].ptr : nullptr,
+                                     cls ? (int32_t*)P.o2[ob].ptr : nullptr,
+                                     hist ? (unsigned long long*)P.hist.ptr : nullptr, P.s_comp))
+      return e;
+    MDC_CUDA(cudaEventRecord(P.e_pass[ob], P.s_comp));
+    MDC_CUDA(cudaStreamWaitEvent(P.s_d2h, P.e_pass[ob], 0));
+    if (probs) MDC_CUDA(cudaMemcpyAsync(probs + p0 * C, P.o0[ob].ptr, (size_t)pm * C * sizeof(float), cudaMemcpyDeviceToHost, P.s_d2h));
+    if (dense) MDC_CUDA(cudaMemcpyAsync(dense + p0 * C, P.o1[ob].ptr, (size_t)pm * C * sizeof(float), cudaMemcpyDeviceToHost, P.s_d2h));
+    if (cls) MDC_CUDA(cudaMemcpyAsync(cls + p0, P.o2[ob].ptr, (size_t)pm * sizeof(int32_t), cudaMemcpyDeviceToHost, P.s_d2h));
+    MDC_CUDA(cudaEventRecord(P.e_pass_d2h[ob], P.s_d2h));
+  }
+  if (hist) {
+    MDC_CUDA(cudaStreamSynchronize(P.s_comp));
+    MDC_CUDA(cudaMemcpyAsync(hist, P.hist.ptr, C * sizeof(unsigned long long), cudaMemcpyDeviceToHost, P.s_d2h));
+  }
+  MDC_CUDA(cudaStreamSynchronize(P.s_d2h));
+  MDC_CUDA(cudaStreamSynchronize(P.s_comp));
+  return MDC_OK;
+}
 
 // ---- confusion matrix ------------------------------------------------------------------
 __global__ void confusion_kernel(const int* __restrict__ t, const int* __restrict__ p, long long n, int C,
@@ -361,6 +426,8 @@ int mdc_predict_f32_host(mdc_handle_t h, const float* x_host, int64_t n, float* 
     if (hist_host) memset(hist_host, 0, h->C * sizeof(unsigned long long));
     return MDC_OK;
   }
+  if (h->model == MDC_MODEL_VT && h->mode != MDC_MODE_FP32)
+    return run_vt_host_pipeline(h, x_host, n, probs_host, dense_host, cls_host, hist_host);
   const int64_t chunk = 16384;
   return run_host_pipeline<float, float, float>(
       h, x_host, n, probs_host, dense_host, cls_host, hist_host, chunk,

@@ -86,6 +86,7 @@ struct mdc_handle_s {
   // work space
   mdc::DeviceBuffer ws_a1;      // padded conv1 activations (fp32 path)
   mdc::DeviceBuffer ws_act;     // conv2 activations
+  size_t vt_act_elems = 0;      // tensor-core paths: activation elements the work space holds per pass
   mdc::DeviceBuffer ws_h;       // dense1 activations (fp32 path)
 
   // ---- Q6.12 ROM images
@@ -108,6 +109,13 @@ int launch_vt_f32(mdc_handle_s* h, const float* x, int64_t n, float* probs, floa
                   int32_t* cls, unsigned long long* hist, cudaStream_t stream);
 int launch_vt_bf16(mdc_handle_s* h, const float* x, int64_t n, float* probs, float* dense,
                    int32_t* cls, unsigned long long* hist, cudaStream_t stream);
+// tensor-core VT-CNN2 path in two stages (the host pipeline copies and convolves chunk by chunk, then runs
+// dense1 + head once per pass)
+int64_t vt_pass_frames(const mdc_handle_s* h);
+int vt_reserve(mdc_handle_s* h, int64_t frames);
+int launch_vt_conv(mdc_handle_s* h, const float* x, int64_t m, int64_t frame_offset, cudaStream_t stream);
+int launch_vt_dense_head(mdc_handle_s* h, int64_t m, float* probs, float* dense, int32_t* cls,
+                         unsigned long long* hist, cudaStream_t stream);
 int pack_tiny(mdc_handle_s* h);
 int pack_vt_f32(mdc_handle_s* h);
 int pack_vt_bf16(mdc_handle_s* h);

@@ -119,60 +119,97 @@ sgemm_bias_act_kernel(ARow arow, const float* __restrict__ B, const float* __res
   }
 }
 
-// logits = h W4 + b4, softmax, argmax, histogram.  One warp per frame.  Shared with vt_bf16.cu.
-__global__ void __launch_bounds__(256)
+constexpr int kHeadThreads = 384;   // 12 warps x <= 170 registers: one block per SM
+// logits = h W4 + b4, softmax, argmax, histogram.  One warp per frame; lane l owns h[8l .. 8l+7] (two 16-B
+// loads) and keeps its 8 x C slice of W4 in registers for the whole (persistent) kernel.  Shared with
+// vt_tensor.cu.
+template <int C>
+__global__ void __launch_bounds__(kHeadThreads, 1)
 vt_head_kernel(const float* __restrict__ hbuf, const float* __restrict__ w4, const float* __restrict__ b4,
-               int C, long long n, float* __restrict__ probs, float* __restrict__ logits_out,
+               long long n, float* __restrict__ probs, float* __restrict__ logits_out,
                int* __restrict__ cls, unsigned long long* __restrict__ hist) {
   const int lane = threadIdx.x & 31;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-  unsigned cnt = 0;
-  for (long long f = warp; f < n; f += nwarps) {
-    float hv[8];
+  float w[8][C], bias[C];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) hv[i] = hbuf[f * 256 + i * 32 + lane];
-    float z[kMaxClasses];
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int c = 0; c < C; ++c) w[i][c] = __ldg(w4 + (lane * 8 + i) * C + c);
+#pragma unroll
+  for (int c = 0; c < C; ++c) bias[c] = __ldg(b4 + c);
+  unsigned cnt = 0;
+  long long f = warp;
+  float4 h0 = make_float4(0.f, 0.f, 0.f, 0.f), h1 = h0;
+  if (f < n) {
+    h0 = __ldcs(reinterpret_cast<const float4*>(hbuf + f * 256) + lane * 2);
+    h1 = __ldcs(reinterpret_cast<const float4*>(hbuf + f * 256) + lane * 2 + 1);
+  }
+  while (f < n) {
+    const long long fn = f + nwarps;
+    float4 n0 = h0, n1 = h1;
+    if (fn < n) {   // next frame of this warp
+      n0 = __ldcs(reinterpret_cast<const float4*>(hbuf + fn * 256) + lane * 2);
+      n1 = __ldcs(reinterpret_cast<const float4*>(hbuf + fn * 256) + lane * 2 + 1);
+    }
+    const float hv[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+    float z[C];
     float m = -3.4e38f;
     int best = 0;
 #pragma unroll
-    for (int c = 0; c < kMaxClasses; ++c) {
-      if (c < C) {
-        float a = 0.f;
+    for (int c = 0; c < C; ++c) {
+      float a = 0.f;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) a = fmaf(hv[i], __ldg(w4 + (i * 32 + lane) * C + c), a);
+      for (int i = 0; i < 8; ++i) a = fmaf(hv[i], w[i][c], a);
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-        z[c] = a + b4[c];
-        if (z[c] > m) { m = z[c]; best = c; }
-      }
+      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+      z[c] = a + bias[c];
+      if (z[c] > m) { m = z[c]; best = c; }
     }
-    float s = 0.f;
+    float e[C], s = 0.f;
 #pragma unroll
-    for (int c = 0; c < kMaxClasses; ++c) if (c < C) s += expf(z[c] - m);
+    for (int c = 0; c < C; ++c) { e[c] = expf(z[c] - m); s += e[c]; }
     const float inv = 1.0f / s;
-    if (lane == 0) {
+    // lane c writes class c: one coalesced 4C-byte store per output instead of C stores from lane 0
+    float zl = z[0], pl = e[0];
 #pragma unroll
-      for (int c = 0; c < kMaxClasses; ++c) {
-        if (c < C) {
-          if (logits_out) logits_out[f * C + c] = z[c];
-          if (probs) probs[f * C + c] = expf(z[c] - m) * inv;
-        }
-      }
-      if (cls) cls[f] = best;
+    for (int c = 1; c < C; ++c) if (lane == c) { zl = z[c]; pl = e[c]; }
+    if (lane < C) {
+      if (logits_out) logits_out[f * C + lane] = zl;
+      if (probs) probs[f * C + lane] = pl * inv;
     }
+    if (lane == 0 && cls) cls[f] = best;
     cnt += (lane == best);
+    h0 = n0; h1 = n1;
+    f = fn;
   }
   if (hist && lane < C && cnt) atomicAdd(hist + lane, (unsigned long long)cnt);
 }
 
+template <int C>
+static void head_launch(unsigned blocks, cudaStream_t stream, const float* hbuf, const float* w4, const float* b4,
+                        long long n, float* probs, float* dense, int* cls, unsigned long long* hist) {
+  vt_head_kernel<C><<<blocks, kHeadThreads, 0, stream>>>(hbuf, w4, b4, n, probs, dense, cls, hist);
+}
+
 int launch_vt_head(mdc_handle_s* h, const float* hbuf, int64_t n, float* probs, float* dense,
                    int32_t* cls, unsigned long long* hist, cudaStream_t stream) {
-  long long blocks = (n * 32 + 255) / 256;
-  const long long maxb = (long long)h->num_sms * 8;
+  long long blocks = (n * 32 + kHeadThreads - 1) / kHeadThreads;
+  const long long maxb = (long long)h->num_sms;
   if (blocks > maxb) blocks = maxb;
-  vt_head_kernel<<<(unsigned)blocks, 256, 0, stream>>>(
-      hbuf, (const float*)h->vt_w4.ptr, (const float*)h->vt_b4.ptr, h->C, n, probs, dense, cls, hist);
+  const float* w4 = (const float*)h->vt_w4.ptr;
+  const float* b4 = (const float*)h->vt_b4.ptr;
+  const unsigned g = (unsigned)blocks;
+  switch (h->C) {
+#define MDC_HEAD_CASE(CC) case CC: head_launch<CC>(g, stream, hbuf, w4, b4, n, probs, dense, cls, hist); break;
+    MDC_HEAD_CASE(1) MDC_HEAD_CASE(2) MDC_HEAD_CASE(3) MDC_HEAD_CASE(4) MDC_HEAD_CASE(5) MDC_HEAD_CASE(6)
+    MDC_HEAD_CASE(7) MDC_HEAD_CASE(8) MDC_HEAD_CASE(9) MDC_HEAD_CASE(10) MDC_HEAD_CASE(11) MDC_HEAD_CASE(12)
+    MDC_HEAD_CASE(13) MDC_HEAD_CASE(14) MDC_HEAD_CASE(15) MDC_HEAD_CASE(16)
+#undef MDC_HEAD_CASE
+    default:
+      set_error("classes=%d outside 1..16", h->C);
+      return MDC_ERR_UNSUPPORTED;
+  }
   h->launches++;
   MDC_CUDA(cudaGetLastError());
   return MDC_OK;

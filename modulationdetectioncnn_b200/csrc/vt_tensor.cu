@@ -937,60 +937,91 @@ int pack_vt_bf16(mdc_handle_s* h) {      // both tensor-core modes (MDC_MODE_BF1
   return MDC_OK;
 }
 
-int launch_vt_bf16(mdc_handle_s* h, const float* x, int64_t n, float* probs, float* dense,
-                   int32_t* cls, unsigned long long* hist, cudaStream_t stream) {
+// frames per pass.  bf16: act = 21 KB/frame -> 1.38 GB; tf32x3: hi + lo fp32 = 84 KB/frame, and
+// 148 x 128 frames is exactly one wave of dense tiles -> 1.6 GB
+int64_t vt_pass_frames(const mdc_handle_s* h) {
+  return h->mode == MDC_MODE_TF32X3 ? (int64_t)h->num_sms * kTM : 65536;
+}
+
+int vt_reserve(mdc_handle_s* h, int64_t frames) {
   const bool tf32 = h->mode == MDC_MODE_TF32X3;
-  // frames per pass.  bf16: act = 21 KB/frame -> 1.38 GB; tf32x3: hi + lo fp32 = 84 KB/frame, and
-  // 148 x 128 frames is exactly one wave of dense tiles -> 1.6 GB
-  const int64_t CH = tf32 ? (int64_t)h->num_sms * kTM : 65536;
-  const int64_t cap = n < CH ? n : CH;
-  if (n == 0) return MDC_OK;
-  const size_t act_elems = (size_t)cap * kVtFlat;
-  if (int e = h->ws_act.reserve(tf32 ? act_elems * 8 : act_elems * 2)) return e;
-  if (int e = h->ws_h.reserve((size_t)cap * kVtH * 4)) return e;
-  void* act0 = h->ws_act.ptr;
-  void* act1 = tf32 ? reinterpret_cast<float*>(h->ws_act.ptr) + act_elems : nullptr;
-  float* hb = reinterpret_cast<float*>(h->ws_h.ptr);
+  const size_t act_elems = (size_t)frames * kVtFlat;
+  if (act_elems > h->vt_act_elems) {
+    if (int e = h->ws_act.reserve(tf32 ? act_elems * 8 : act_elems * 2)) return e;
+    if (int e = h->ws_h.reserve((size_t)frames * kVtH * 4)) return e;
+    h->vt_act_elems = act_elems;
+  }
+  return MDC_OK;
+}
+
+// conv1 + conv2 of m frames at x -> activations of frames [frame_offset, frame_offset + m) of the pass
+int launch_vt_conv(mdc_handle_s* h, const float* x, int64_t m, int64_t frame_offset, cudaStream_t stream) {
+  const bool tf32 = h->mode == MDC_MODE_TF32X3;
+  if (m == 0) return MDC_OK;
+  const size_t off = (size_t)frame_offset * kVtFlat;
+  void* act0 = tf32 ? (void*)(reinterpret_cast<float*>(h->ws_act.ptr) + off)
+                    : (void*)(reinterpret_cast<__nv_bfloat16*>(h->ws_act.ptr) + off);
+  void* act1 = tf32 ? (void*)(reinterpret_cast<float*>(h->ws_act.ptr) + h->vt_act_elems + off) : nullptr;
   ConvW1 w1c;
   static_assert(sizeof(ConvW1) == 32 * 32 * sizeof(float), "conv1 image size");
   memcpy(&w1c, h->vt_w1_img.data(), sizeof(w1c));
   static const int dbg = getenv("MDC_VT_DEBUG") ? atoi(getenv("MDC_VT_DEBUG")) : 0;   // timing experiments
+  const long long out_rows = tf32 ? ConvCfg<true>::kOutRows : ConvCfg<false>::kOutRows;
+  const long long num_st = (m * 132 + out_rows - 1) / out_rows;
+  const long long pairs_needed = (num_st + 1) / 2, pairs_max = h->num_sms / 2;
+  const unsigned grid_c = 2u * (unsigned)(pairs_needed < pairs_max ? pairs_needed : pairs_max);
+  const float* b2 = reinterpret_cast<const float*>(h->vt_b2.ptr);
+  const uint8_t* w2 = reinterpret_cast<const uint8_t*>(h->vt_w2_bf16.ptr);
+  prof_begin(h, stream);
+  if (tf32)
+    vt_conv_kernel<true><<<grid_c, ConvCfg<true>::kThreads, ConvCfg<true>::total, stream>>>(w1c, x, m, b2, w2, act0, act1, num_st, dbg);
+  else
+    vt_conv_kernel<false><<<grid_c, ConvCfg<false>::kThreads, ConvCfg<false>::total, stream>>>(w1c, x, m, b2, w2, act0, act1, num_st, dbg);
+  prof_end(h, stream);
+  h->launches += 1;
+  MDC_CUDA(cudaGetLastError());
+  return MDC_OK;
+}
+
+// dense1 + Dense(C) + softmax over the first m frames of the pass
+int launch_vt_dense_head(mdc_handle_s* h, int64_t m, float* probs, float* dense, int32_t* cls,
+                         unsigned long long* hist, cudaStream_t stream) {
+  const bool tf32 = h->mode == MDC_MODE_TF32X3;
+  if (m == 0) return MDC_OK;
+  float* hb = reinterpret_cast<float*>(h->ws_h.ptr);
   const CUtensorMap* wmaps = reinterpret_cast<const CUtensorMap*>(h->tmap_w3);
+  const float* b3 = reinterpret_cast<const float*>(h->vt_b3.ptr);
+  if (!tf32) {
+    CUtensorMap map_a;
+    if (int e = make_kmajor_map(&map_a, h->ws_act.ptr, (uint64_t)m, false, kDM)) return e;
+    const int tiles = (int)((m + kDM - 1) / kDM);
+    const unsigned grid_d = (unsigned)(tiles < h->num_sms ? tiles : h->num_sms);
+    vt_dense_bf16_kernel<<<grid_d, kDenseThreads, DenseSmem::total, stream>>>(map_a, wmaps[0], b3, hb, m, tiles);
+  } else {
+    CUtensorMap map_ah, map_al;
+    const float* act = reinterpret_cast<const float*>(h->ws_act.ptr);
+    if (int e = make_kmajor_map(&map_ah, act, (uint64_t)m, true, kTM)) return e;
+    if (int e = make_kmajor_map(&map_al, act + h->vt_act_elems, (uint64_t)m, true, kTM)) return e;
+    const int tiles = (int)((m + kTM - 1) / kTM);
+    const unsigned grid_d = (unsigned)(tiles < h->num_sms ? tiles : h->num_sms);
+    vt_dense_tf32x3_kernel<<<grid_d, kDenseT32Threads, DenseT32Smem::total, stream>>>(map_ah, map_al, wmaps[0], wmaps[1],
+                                                                                       b3, hb, m, tiles);
+  }
+  h->launches += 1;
+  MDC_CUDA(cudaGetLastError());
+  return launch_vt_head(h, hb, m, probs, dense, cls, hist, stream);
+}
+
+int launch_vt_bf16(mdc_handle_s* h, const float* x, int64_t n, float* probs, float* dense,
+                   int32_t* cls, unsigned long long* hist, cudaStream_t stream) {
+  if (n == 0) return MDC_OK;
+  const int64_t CH = vt_pass_frames(h);
+  if (int e = vt_reserve(h, n < CH ? n : CH)) return e;
   for (int64_t s = 0; s < n; s += CH) {
     const int64_t m = (n - s) < CH ? (n - s) : CH;
-    const long long out_rows = tf32 ? ConvCfg<true>::kOutRows : ConvCfg<false>::kOutRows;
-    const long long num_st = (m * 132 + out_rows - 1) / out_rows;
-    const long long pairs_needed = (num_st + 1) / 2, pairs_max = h->num_sms / 2;
-    const unsigned grid_c = 2u * (unsigned)(pairs_needed < pairs_max ? pairs_needed : pairs_max);
-    const float* b2 = reinterpret_cast<const float*>(h->vt_b2.ptr);
-    const uint8_t* w2 = reinterpret_cast<const uint8_t*>(h->vt_w2_bf16.ptr);
-    prof_begin(h, stream);
-    if (tf32)
-      vt_conv_kernel<true><<<grid_c, ConvCfg<true>::kThreads, ConvCfg<true>::total, stream>>>(w1c, x + s * 256, m, b2, w2, act0, act1, num_st, dbg);
-    else
-      vt_conv_kernel<false><<<grid_c, ConvCfg<false>::kThreads, ConvCfg<false>::total, stream>>>(w1c, x + s * 256, m, b2, w2, act0, act1, num_st, dbg);
-    prof_end(h, stream);
-    MDC_CUDA(cudaGetLastError());
-    const float* b3 = reinterpret_cast<const float*>(h->vt_b3.ptr);
-    if (!tf32) {
-      CUtensorMap map_a;
-      if (int e = make_kmajor_map(&map_a, act0, (uint64_t)m, false, kDM)) return e;
-      const int tiles = (int)((m + kDM - 1) / kDM);
-      const unsigned grid_d = (unsigned)(tiles < h->num_sms ? tiles : h->num_sms);
-      vt_dense_bf16_kernel<<<grid_d, kDenseThreads, DenseSmem::total, stream>>>(map_a, wmaps[0], b3, hb, m, tiles);
-    } else {
-      CUtensorMap map_ah, map_al;
-      if (int e = make_kmajor_map(&map_ah, act0, (uint64_t)m, true, kTM)) return e;
-      if (int e = make_kmajor_map(&map_al, act1, (uint64_t)m, true, kTM)) return e;
-      const int tiles = (int)((m + kTM - 1) / kTM);
-      const unsigned grid_d = (unsigned)(tiles < h->num_sms ? tiles : h->num_sms);
-      vt_dense_tf32x3_kernel<<<grid_d, kDenseT32Threads, DenseT32Smem::total, stream>>>(map_ah, map_al, wmaps[0], wmaps[1],
-                                                                                         b3, hb, m, tiles);
-    }
-    h->launches += 2;
-    MDC_CUDA(cudaGetLastError());
-    if (int e = launch_vt_head(h, hb, m, probs ? probs + s * h->C : nullptr, dense ? dense + s * h->C : nullptr,
-                               cls ? cls + s : nullptr, hist, stream))
+    if (int e = launch_vt_conv(h, x + s * 256, m, 0, stream)) return e;
+    if (int e = launch_vt_dense_head(h, m, probs ? probs + s * h->C : nullptr, dense ? dense + s * h->C : nullptr,
+                                     cls ? cls + s : nullptr, hist, stream))
       return e;
   }
   return MDC_OK;
