@@ -513,9 +513,22 @@ struct DenseSmem {
 };
 static_assert(DenseSmem::total <= 232448, "dense kernel shared memory exceeds 227 KB");
 
+// Dense(C) weights as a kernel parameter (constant bank): in the fused epilogue every W4 element is an
+// immediate-offset constant operand of an FFMA, no shared-memory or global loads.  [256][C] fp32 + bias.
+template <int C>
+struct HeadW {
+  float w[256 * C];
+  float b[C];
+};
+
+// The epilogue is the rest of the network: thread = frame, so +b3, ReLU, Dense(C), softmax, argmax and the
+// class histogram need no cross-lane traffic and h never goes to HBM (hbuf != NULL keeps a copy for debugging).
+template <int C>
 __global__ void __launch_bounds__(kDenseThreads, 1)
 vt_dense_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                     const float* __restrict__ b3g, float* __restrict__ hbuf, long long n, int num_tiles) {
+                     const __grid_constant__ HeadW<C> hw, const float* __restrict__ b3g, float* __restrict__ hbuf,
+                     long long n, int num_tiles, float* __restrict__ probs, float* __restrict__ logits_out,
+                     int* __restrict__ cls, unsigned long long* __restrict__ hist) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DenseSmem::bars);
@@ -589,44 +602,69 @@ vt_dense_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     const int q = warp & 3, m = (warp - 2) >> 2;
     const float* b3s = reinterpret_cast<const float*>(smem + DenseSmem::b3);
     uint32_t k = 0;
+    unsigned cnt = 0;                             // lane c counts class c
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++k) {
       mbar_wait(tmem_full, k & 1);
       tc_fence_after_sync();
       const long long row = (long long)tile * kDM + m * 128 + q * 32 + lane;
-      float* dst = hbuf + row * 256;
-#pragma unroll 1
+      float z[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) z[c] = hw.b[c];
+#pragma unroll
       for (int cc = 0; cc < 16; cc += 2) {
         uint32_t v0[16], v1[16];
         tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + m * 256 + cc * 16, v0);
         tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + m * 256 + cc * 16 + 16, v1);
         tmem_ld_wait();
-        if (row < n) {
+        float hv[32];
 #pragma unroll
-          for (int e = 0; e < 16; e += 4) {
-            const int c0 = cc * 16 + e;
-            float4 o;
-            o.x = fmaxf(__uint_as_float(v0[e]) + b3s[c0], 0.f);
-            o.y = fmaxf(__uint_as_float(v0[e + 1]) + b3s[c0 + 1], 0.f);
-            o.z = fmaxf(__uint_as_float(v0[e + 2]) + b3s[c0 + 2], 0.f);
-            o.w = fmaxf(__uint_as_float(v0[e + 3]) + b3s[c0 + 3], 0.f);
-            *reinterpret_cast<float4*>(dst + c0) = o;
-          }
+        for (int e = 0; e < 16; ++e) {
+          hv[e] = fmaxf(__uint_as_float(v0[e]) + b3s[cc * 16 + e], 0.f);
+          hv[16 + e] = fmaxf(__uint_as_float(v1[e]) + b3s[cc * 16 + 16 + e], 0.f);
+        }
 #pragma unroll
-          for (int e = 0; e < 16; e += 4) {
-            const int c0 = cc * 16 + 16 + e;
-            float4 o;
-            o.x = fmaxf(__uint_as_float(v1[e]) + b3s[c0], 0.f);
-            o.y = fmaxf(__uint_as_float(v1[e + 1]) + b3s[c0 + 1], 0.f);
-            o.z = fmaxf(__uint_as_float(v1[e + 2]) + b3s[c0 + 2], 0.f);
-            o.w = fmaxf(__uint_as_float(v1[e + 3]) + b3s[c0 + 3], 0.f);
-            *reinterpret_cast<float4*>(dst + c0) = o;
-          }
+        for (int e = 0; e < 32; ++e)
+#pragma unroll
+          for (int c = 0; c < C; ++c) z[c] = fmaf(hv[e], hw.w[(cc * 16 + e) * C + c], z[c]);
+        if (hbuf != nullptr && row < n) {
+#pragma unroll
+          for (int e = 0; e < 32; e += 4)
+            *reinterpret_cast<float4*>(hbuf + row * 256 + cc * 16 + e) = make_float4(hv[e], hv[e + 1], hv[e + 2], hv[e + 3]);
         }
       }
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(tmem_empty);
+      // softmax / argmax of this thread's frame
+      float mx = z[0];
+      int best = 0;
+#pragma unroll
+      for (int c = 1; c < C; ++c) if (z[c] > mx) { mx = z[c]; best = c; }
+      if (row >= n) best = -1;
+      if (row < n) {
+        if (logits_out) {
+#pragma unroll
+          for (int c = 0; c < C; ++c) logits_out[row * C + c] = z[c];
+        }
+        if (probs) {
+          float e[C], sum = 0.f;
+#pragma unroll
+          for (int c = 0; c < C; ++c) { e[c] = expf(z[c] - mx); sum += e[c]; }
+          const float inv = 1.0f / sum;
+#pragma unroll
+          for (int c = 0; c < C; ++c) probs[row * C + c] = e[c] * inv;
+        }
+        if (cls) cls[row] = best;
+      }
+      if (hist) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          const unsigned votes = __popc(__ballot_sync(0xffffffffu, best == c));
+          if (lane == c) cnt += votes;
+        }
+      }
     }
+    if (hist && lane < C && cnt) atomicAdd(hist + lane, (unsigned long long)cnt);
   }
 
   __syncwarp();
@@ -932,7 +970,6 @@ int pack_vt_bf16(mdc_handle_s* h) {      // both tensor-core modes (MDC_MODE_BF1
   }
   MDC_CUDA(cudaFuncSetAttribute(vt_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<false>::total));
   MDC_CUDA(cudaFuncSetAttribute(vt_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<true>::total));
-  MDC_CUDA(cudaFuncSetAttribute(vt_dense_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DenseSmem::total));
   MDC_CUDA(cudaFuncSetAttribute(vt_dense_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DenseT32Smem::total));
   return MDC_OK;
 }
@@ -983,6 +1020,38 @@ int launch_vt_conv(mdc_handle_s* h, const float* x, int64_t m, int64_t frame_off
   return MDC_OK;
 }
 
+template <int C>
+static int dense_bf16_launch(mdc_handle_s* h, unsigned grid, cudaStream_t stream, const CUtensorMap& map_a,
+                             const CUtensorMap& map_b, const float* b3, float* hb, int64_t m, int tiles, float* probs,
+                             float* dense, int32_t* cls, unsigned long long* hist) {
+  static bool attr_set[16] = {};                 // per device
+  if (!attr_set[h->device & 15]) {
+    MDC_CUDA(cudaFuncSetAttribute(vt_dense_bf16_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, DenseSmem::total));
+    attr_set[h->device & 15] = true;
+  }
+  HeadW<C> hw;
+  memcpy(hw.w, h->w[MDC_T_DENSE2_K].data(), sizeof(hw.w));     // Keras (256, C) row-major
+  memcpy(hw.b, h->w[MDC_T_DENSE2_B].data(), sizeof(hw.b));
+  vt_dense_bf16_kernel<C><<<grid, kDenseThreads, DenseSmem::total, stream>>>(map_a, map_b, hw, b3, hb, m, tiles, probs,
+                                                                            dense, cls, hist);
+  return MDC_OK;
+}
+
+static int dense_bf16_dispatch(mdc_handle_s* h, unsigned grid, cudaStream_t stream, const CUtensorMap& map_a,
+                               const CUtensorMap& map_b, const float* b3, float* hb, int64_t m, int tiles, float* probs,
+                               float* dense, int32_t* cls, unsigned long long* hist) {
+  switch (h->C) {
+#define MDC_DENSE_CASE(CC) \
+  case CC: return dense_bf16_launch<CC>(h, grid, stream, map_a, map_b, b3, hb, m, tiles, probs, dense, cls, hist);
+    MDC_DENSE_CASE(1) MDC_DENSE_CASE(2) MDC_DENSE_CASE(3) MDC_DENSE_CASE(4) MDC_DENSE_CASE(5) MDC_DENSE_CASE(6)
+    MDC_DENSE_CASE(7) MDC_DENSE_CASE(8) MDC_DENSE_CASE(9) MDC_DENSE_CASE(10) MDC_DENSE_CASE(11) MDC_DENSE_CASE(12)
+    MDC_DENSE_CASE(13) MDC_DENSE_CASE(14) MDC_DENSE_CASE(15) MDC_DENSE_CASE(16)
+#undef MDC_DENSE_CASE
+  }
+  set_error("classes=%d outside 1..16", h->C);
+  return MDC_ERR_UNSUPPORTED;
+}
+
 // dense1 + Dense(C) + softmax over the first m frames of the pass
 int launch_vt_dense_head(mdc_handle_s* h, int64_t m, float* probs, float* dense, int32_t* cls,
                          unsigned long long* hist, cudaStream_t stream) {
@@ -996,7 +1065,13 @@ int launch_vt_dense_head(mdc_handle_s* h, int64_t m, float* probs, float* dense,
     if (int e = make_kmajor_map(&map_a, h->ws_act.ptr, (uint64_t)m, false, kDM)) return e;
     const int tiles = (int)((m + kDM - 1) / kDM);
     const unsigned grid_d = (unsigned)(tiles < h->num_sms ? tiles : h->num_sms);
-    vt_dense_bf16_kernel<<<grid_d, kDenseThreads, DenseSmem::total, stream>>>(map_a, wmaps[0], b3, hb, m, tiles);
+    static const bool keep_h = getenv("MDC_VT_KEEP_H") != nullptr;       // debugging: also store dense1 activations
+    if (int e = dense_bf16_dispatch(h, grid_d, stream, map_a, wmaps[0], b3, keep_h ? hb : nullptr, m, tiles, probs, dense,
+                                    cls, hist))
+      return e;
+    h->launches += 1;
+    MDC_CUDA(cudaGetLastError());
+    return MDC_OK;
   } else {
     CUtensorMap map_ah, map_al;
     const float* act = reinterpret_cast<const float*>(h->ws_act.ptr);
