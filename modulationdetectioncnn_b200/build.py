@@ -40,6 +40,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(build_dir, exist_ok=True)
     procs = []
     flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
+    flags += os.environ.get("MDC_NVCC_EXTRA", "").split()          # e.g. -DMDC_VT_ABLATE for timing experiments
     for src in SOURCES:
         obj = os.path.join(build_dir, src.replace(".cu", ".o"))
         objs.append(obj)

@@ -328,7 +328,7 @@ int mdc_destroy(mdc_handle_t h) {
   for (auto& pr : h->prof.pending) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
   DeviceBuffer* bufs[] = {&h->tiny_conv, &h->tiny_dense, &h->tiny_bias, &h->vt_w1, &h->vt_b1, &h->vt_w2,
                           &h->vt_b2, &h->vt_w3, &h->vt_b3, &h->vt_w4, &h->vt_b4, &h->vt_w2_bf16,
-                          &h->vt_w3_bf16, &h->ws_a1, &h->ws_act, &h->ws_h, &h->q_dense};
+                          &h->vt_w3_bf16, &h->vt_w2_n240, &h->ws_a1, &h->ws_act, &h->ws_h, &h->q_dense};
   for (DeviceBuffer* b : bufs) b->release();
   free(h->tmap_w3);
   delete h;

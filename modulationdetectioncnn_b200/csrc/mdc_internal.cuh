@@ -80,7 +80,7 @@ struct mdc_handle_s {
   // VT fp32 path
   mdc::DeviceBuffer vt_w1, vt_b1, vt_w2, vt_b2, vt_w3, vt_b3, vt_w4, vt_b4;
   // VT bf16 path (packed operand images)
-  mdc::DeviceBuffer vt_w2_bf16, vt_w3_bf16;
+  mdc::DeviceBuffer vt_w2_bf16, vt_w3_bf16, vt_w2_n240;
   std::vector<float> vt_w1_img;  // conv1 weights as the conv kernel's by-value parameter (4 KB)
   void* tmap_w3 = nullptr;      // CUtensorMap (host copy, 128 B)
   // work space

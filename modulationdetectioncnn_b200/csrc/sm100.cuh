@@ -73,12 +73,16 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
   while (!mbar_try_wait_cluster(bar, parity)) {
   }
 }
-// arrive on the barrier at the same shared-memory offset in CTA `rank` of this cluster
+// arrive on the barrier at the same shared-memory offset in CTA `rank` of this cluster.  Default (.release.cta)
+// semantics on purpose: the .release.cluster form compiles to MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR (hundreds of
+// cycles per arrive, it set the pace of the conv kernels' chunk loop), and what these arrivals order is
+// shared-memory / TMEM traffic already fenced for the async proxy (fence.proxy.async, tcgen05.fence) by the
+// arriving warp - the same protocol CUTLASS's ClusterBarrier::arrive(cta_id) uses.
 __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
   asm volatile(
       "{\n\t.reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)),
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)),
       "r"(rank)
       : "memory");
 }
@@ -192,6 +196,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
         "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(taddr));
+}
+// the same shape, 8 consecutive columns
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr));
 }
 // the same shape, 32 consecutive columns
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {

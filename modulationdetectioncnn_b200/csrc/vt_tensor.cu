@@ -254,12 +254,10 @@ vt_conv_kernel(const __grid_constant__ ConvW1 w1c, const float* __restrict__ x, 
         const uint32_t buf = k % kAccBufs, use = k / kAccBufs;
         const uint32_t acc = tmem + buf * kAccCols;
         mbar_wait(&tmem_empty[buf], (use & 1) ^ 1);          // both epilogues drained this buffer
-        mbar_wait_cluster(&tmem_empty[buf], (use & 1) ^ 1);
         tc_fence_after_sync();
         for (int c = 0; c < kChunks; ++c, ++it) {
           const uint32_t s = it % kStages, ph = (it / kStages) & 1;
-          mbar_wait(&full[s], ph);               // cheap cta-scope spin ...
-          mbar_wait_cluster(&full[s], ph);       // ... then one cluster-scope acquire (the peer's relay)
+          mbar_wait(&full[s], ph);               // own producers, own TMA and the peer's relay
           tc_fence_after_sync();
           if (elect_one()) {
             const uint32_t a_lo = smem_desc_lo(a_base + s * kASlot, kALbo);
@@ -481,6 +479,383 @@ vt_conv_kernel(const __grid_constant__ ConvW1 w1c, const float* __restrict__ x, 
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&full[(it - 1) % kStages]);
+    }
+  }
+
+  // ---- teardown (the pair leaves together: the leader's MMAs read the peer's shared memory)
+  __syncwarp();
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 0) tmem_dealloc_pair<512>(tmem);
+}
+
+// ------------------------------------------------------------------------------------------
+// bf16 conv kernel, second formulation ("N240"): the three conv2 taps become N instead of K.
+//
+// The kernel above fetches every conv1 activation tile from shared memory three times (once per tap, the
+// descriptor shifted by one row) and its N = 80 MMAs are operand-fetch-bound: 45 cycles per M=256 x N=80 x
+// K=16 MMA against a 40-cycle math floor, and with the producers' stores and the epilogue staging the
+// kernel runs at 90 % of the 128 B/clk shared-memory bandwidth.  Here one MMA computes all three taps'
+// partial products for a K step, P[row][tap*80 + o] = A[row][:] . W2[tap][:, o]   (N = 240: 120 cycles of
+// math, 62 of operand fetch - math-bound, measured 120.0, tools/umma2_probe.cu), and the epilogue adds the
+// three partials of an output row from three consecutive accumulator rows:
+//     out[r][o] = P[r][o] + P[r+1][80 + o] + P[r+2][160 + o]
+// (TMEM row = lane, so row r+1 is a warp shuffle; the two rows a warp needs from the next lane quarter go
+// through a 960-B shared-memory exchange).  A is read once per K step, W2 (123 KB per CTA of the pair) stays
+// resident in shared memory for the whole kernel, and the MMA count drops 3x.
+//
+// Geometry: CTA pair (cta_group::2, M = 256), one 128-row tape tile per CTA per iteration (126 outputs,
+// 2-row halo), accumulators 2 x 240 TMEM columns (double-buffered), 16 K chunks of 16 channels x {I,Q}.
+// 18 warps: TMA, MMA, 8 epilogue (lane quarter x column half: a tile is only 3,840 MMA cycles, one warp per
+// quarter needs ~10,000 for the 240-column shift-add), 8 conv1 producers (32-row block x chunk phase).
+struct Conv240 {
+  static constexpr int kRows = 128;
+  static constexpr int kOutRows = kRows - 2;
+  static constexpr int kALbo = kRows * 16;                 // bytes between K groups of the A image
+  static constexpr int kChunks = 16;
+  static constexpr int kStages = 6;
+  static constexpr int kASlot = kGroups * kALbo;           // 8,192
+  static constexpr int kBRows = 120;                       // accumulator columns (tap*80 + o) held per CTA
+  static constexpr int kBLbo = kBRows * 16;
+  static constexpr int kBChunk = kGroups * kBLbo;          // 7,680
+  static constexpr int kBBytes = kChunks * kBChunk;        // 122,880 resident
+  static constexpr int kXF = 2;                            // frames a 128-row tile can touch
+  static constexpr int kEpiWarps = 8;                      // (TMEM lane quarter) x (column half)
+  static constexpr int kProd0 = 2 + kEpiWarps;             // first producer warp
+  static constexpr int kPhases = 2;                        // a producer warp handles every kPhases-th chunk
+  static constexpr int kProdWarps = 4 * kPhases;           // (32-row block) x (chunk phase)
+  static constexpr int kThreads = (kProd0 + kProdWarps) * 32;
+  static constexpr int kAccCols = 240;
+  static constexpr int kOutBytes = kOutRows * 160;         // 20,160: one staged bf16 output tile
+  static constexpr int kXchFloats = 240;                   // per warp: P1 of lane 0, P2 of lane 0, P2 of lane 1
+  // shared memory map
+  static constexpr int b = 0;
+  static constexpr int a = b + kBBytes;
+  static constexpr int xs = a + kStages * kASlot;
+  static constexpr int out = xs + 2 * kXF * 1024;
+  static constexpr int xch = out + 2 * 128 * 160;
+  static constexpr int b2 = xch + 2 * 4 * kXchFloats * 4;
+  static constexpr int bars = b2 + 320;
+  // full[S], empty[S], b_full, b_peer, x_full[2], x_empty[2], tmem_full[2], tmem_empty[2]
+  static constexpr int nbars = 2 * kStages + 2 + 4 + 4;
+  static constexpr int tmem_slot = bars + nbars * 8;
+  static constexpr int total = tmem_slot + 16;
+};
+static_assert(Conv240::total <= 232448, "N240 conv kernel shared memory exceeds 227 KB");
+
+// producer main loop of the warps with chunk phase CP: chunks CP, CP + kPhases, ... of every tile, all four K
+// groups of one tape row per thread (CP is compile-time, so conv1 weights are immediate constant-bank
+// operands).
+template <int CP>
+__device__ __forceinline__ void conv240_produce(const ConvW1& w1c, const uint64_t (&xd)[2][3], uint32_t m, uint8_t* arow0,
+                                                uint64_t* full, uint64_t* empty, uint32_t tile_k, uint32_t& prev, int lane,
+                                                uint32_t rank, int dbg, long long* trace) {
+#pragma unroll
+  for (int i = 0; i < Conv240::kChunks / Conv240::kPhases; ++i) {
+    const int c = Conv240::kPhases * i + CP;
+    uint4 o[kGroups];
+#pragma unroll
+    for (int hc = 0; hc < 2; ++hc) {
+      if (dbg & 1) break;
+      const unsigned long long* w = &w1c.v[(c * 2 + hc) * 16];
+      o[2 * hc] = conv1_item(xd[0][0], xd[0][1], xd[0][2], w, m);
+      o[2 * hc + 1] = conv1_item(xd[1][0], xd[1][1], xd[1][2], w, m);
+    }
+    if (prev != 0xFFFFFFFFu) {       // publish this warp's previous chunk: its stores were issued a chunk of math ago
+      if (!(dbg & 8)) fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        if (rank == 0) mbar_arrive(&full[prev]);
+        else mbar_arrive_remote(&full[prev], 0);
+      }
+    }
+    const uint32_t it = tile_k * Conv240::kChunks + c;
+    const uint32_t s = it % Conv240::kStages, ph = (it / Conv240::kStages) & 1;
+    if (trace && lane == 0 && (tile_k * 8 + i) < 128) trace[2 * 512 + (tile_k * 8 + i) * 4] = clock64();
+    mbar_wait(&empty[s], ph ^ 1);
+    if (trace && lane == 0 && (tile_k * 8 + i) < 128) trace[2 * 512 + (tile_k * 8 + i) * 4 + 1] = clock64();
+    if (!(dbg & 1)) {
+#pragma unroll
+      for (int g = 0; g < kGroups; ++g) *reinterpret_cast<uint4*>(arow0 + s * Conv240::kASlot + g * Conv240::kALbo) = o[g];
+    }
+    prev = s;
+  }
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Conv240::kThreads, 1)
+vt_conv240_kernel(const __grid_constant__ ConvW1 w1c, const float* __restrict__ x, long long n,
+                  const float* __restrict__ b2g, const uint8_t* __restrict__ w2img, __nv_bfloat16* __restrict__ act,
+                  long long num_tiles, int dbg_rt, long long* __restrict__ trace) {
+  using Cfg = Conv240;
+#ifdef MDC_VT_ABLATE   // role-ablation flags for timing experiments (results are garbage): see vt_conv_kernel
+  const int dbg = dbg_rt;
+  // clock64 trace of CTA 0 (ablate builds): trace[role * 512 + i]
+#define MDC_TRACE(role, i) do { if (trace && blockIdx.x == 0 && (i) < 512) trace[(role) * 512 + (i)] = clock64(); } while (0)
+#else
+  constexpr int dbg = 0;
+#define MDC_TRACE(role, i) do { } while (0)
+#endif
+  constexpr int kStages = Cfg::kStages, kChunks = Cfg::kChunks, kProdWarps = Cfg::kProdWarps;
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::bars);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kStages;
+  uint64_t* b_full = bars + 2 * kStages;
+  uint64_t* b_peer = b_full + 1;           // (leader's only) the peer CTA's W2 half is resident
+  uint64_t* x_full = b_peer + 1;           // [2] frame buffers
+  uint64_t* x_empty = x_full + 2;          // [2]
+  uint64_t* tmem_full = x_empty + 2;       // [2] accumulator buffers
+  uint64_t* tmem_empty = tmem_full + 2;    // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + Cfg::tmem_slot);
+
+  const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
+  const long long total_rows = n * 132;
+  const uint32_t rank = cluster_ctarank();                 // 0 = leader (issues the pair's MMAs)
+  const long long t_first = 2ll * cluster_id_x(), t_step = 2ll * cluster_count_x();
+
+  for (int i = tid; i < 80; i += Cfg::kThreads) reinterpret_cast<float*>(smem + Cfg::b2)[i] = b2g[i];
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full[s], 8);                 // (leader's only) the four row-block warps of the chunk's phase in each CTA
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(b_full, 1);
+    mbar_init(b_peer, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&x_full[b], 1);
+      mbar_init(&x_empty[b], kProdWarps);
+      mbar_init(&tmem_full[b], 1);
+      mbar_init(&tmem_empty[b], 2 * Cfg::kEpiWarps);   // (leader's only) the epilogue warps of both CTAs
+    }
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc_pair<512>(tmem_slot);
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA: this CTA's half of W2 (once), then the frames of every tile
+    if (elect_one()) {
+      mbar_arrive_expect_tx(b_full, Cfg::kBBytes);
+      const uint8_t* src = w2img + (size_t)rank * Cfg::kBBytes;
+      for (int c = 0; c < kChunks; ++c)
+        bulk_g2s(smem + Cfg::b + c * Cfg::kBChunk, src + (size_t)c * Cfg::kBChunk, Cfg::kBChunk, b_full);
+    }
+    __syncwarp();
+    uint32_t k = 0;
+    for (long long base = t_first; base < num_tiles; base += t_step, ++k) {
+      const long long f0 = ((base + rank) * Cfg::kOutRows) / 132;
+      const long long left = n - f0;
+      const uint32_t nf = left <= 0 ? 0u : (left < Cfg::kXF ? (uint32_t)left : (uint32_t)Cfg::kXF);
+      const uint32_t b = k & 1;
+      mbar_wait(&x_empty[b], ((k >> 1) & 1) ^ 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&x_full[b], nf * 1024);
+        if (nf) bulk_g2s(smem + Cfg::xs + b * (Cfg::kXF * 1024), x + f0 * 256, nf * 1024, &x_full[b]);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (leader CTA only; the peer's warp 1 just reports its W2 half resident)
+    uint32_t it = 0, k = 0;
+    mbar_wait(b_full, 0);                        // this CTA's W2 half has landed
+    if (rank == 0) {
+      mbar_wait(b_peer, 0);                      // ... and the peer's
+      const uint32_t idesc = make_idesc_bf16(256, 240);
+      const uint32_t a_base = smem_u32(smem + Cfg::a), b_base = smem_u32(smem + Cfg::b);
+      constexpr uint32_t hi = smem_desc_hi(128, 0);
+      for (long long base = t_first; base < num_tiles; base += t_step, ++k) {
+        const uint32_t buf = k & 1;
+        const uint32_t acc = tmem + buf * Cfg::kAccCols;
+        mbar_wait(&tmem_empty[buf], ((k >> 1) & 1) ^ 1);     // both epilogues drained this buffer
+        tc_fence_after_sync();
+#pragma unroll 1
+        for (int c = 0; c < kChunks; ++c, ++it) {
+          const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+          mbar_wait(&full[s], ph);               // the producers of both CTAs have published this stage
+          tc_fence_after_sync();
+          if (lane == 0) MDC_TRACE(0, it);
+          if (elect_one()) {
+            const uint32_t a_lo = smem_desc_lo(a_base + s * Cfg::kASlot, Cfg::kALbo);
+            const uint32_t b_lo = smem_desc_lo(b_base + c * Cfg::kBChunk, Cfg::kBLbo);
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks)
+              if (!(dbg & 2)) mma_bf16_ss_pair(acc, desc64(a_lo + ((2 * ks * Cfg::kALbo) >> 4), hi),
+                               desc64(b_lo + ((2 * ks * Cfg::kBLbo) >> 4), hi), idesc, (c | ks) != 0);
+            mma_commit_pair(&empty[s]);
+            if (c == kChunks - 1) mma_commit_pair(&tmem_full[buf]);
+          }
+          __syncwarp();
+        }
+      }
+    } else {
+      if (elect_one()) mbar_arrive_remote(b_peer, 0);
+      __syncwarp();
+    }
+  } else if (warp < Cfg::kProd0) {
+    // ================= epilogue: shift-add the three taps, +bias, ReLU -> bf16 tile in smem -> bulk store.
+    // warp = (TMEM lane quarter q, column half hf): output channels 40 hf .. 40 hf + 39 of rows 32 q .. 32 q + 31
+    const int q = warp & 3, hf = (warp - 2) >> 2;
+    const bool leader = (warp == 2 && lane == 0);
+    constexpr int kEpiThreads = Cfg::kEpiWarps * 32;
+    const float* b2s = reinterpret_cast<const float*>(smem + Cfg::b2) + hf * 40;
+    float* xch = reinterpret_cast<float*>(smem + Cfg::xch);
+    uint32_t k = 0;
+    for (long long base = t_first; base < num_tiles; base += t_step, ++k) {
+      const long long row_lo = (base + rank) * Cfg::kOutRows;
+      const uint32_t buf = k & 1;
+      uint8_t* obuf = smem + Cfg::out + buf * (128 * 160);
+      float* xw = xch + ((k & 1) * 4 + q) * Cfg::kXchFloats + hf * 120;   // [P1 lane 0 | P2 lane 0 | P2 lane 1] x 40
+      mbar_wait(&tmem_full[buf], (k >> 1) & 1);
+      tc_fence_after_sync();
+      if (warp == 2 && lane == 0) MDC_TRACE(1, 4 * k);
+      const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + buf * Cfg::kAccCols + hf * 40;
+      // pass 1: lanes 0 and 1 publish the tap-1 / tap-2 partials the previous lane quarter needs
+      if (!(dbg & 4)) {
+        uint32_t p1[5][8], p2[5][8];
+#pragma unroll
+        for (int g = 0; g < 5; ++g) {
+          tmem_ld8(tbase + 80 + g * 8, p1[g]);
+          tmem_ld8(tbase + 160 + g * 8, p2[g]);
+        }
+        tmem_ld_wait();
+        if (lane == 0) {
+#pragma unroll
+          for (int g = 0; g < 5; ++g) {
+            *reinterpret_cast<uint4*>(xw + g * 8) = make_uint4(p1[g][0], p1[g][1], p1[g][2], p1[g][3]);
+            *reinterpret_cast<uint4*>(xw + g * 8 + 4) = make_uint4(p1[g][4], p1[g][5], p1[g][6], p1[g][7]);
+            *reinterpret_cast<uint4*>(xw + 40 + g * 8) = make_uint4(p2[g][0], p2[g][1], p2[g][2], p2[g][3]);
+            *reinterpret_cast<uint4*>(xw + 40 + g * 8 + 4) = make_uint4(p2[g][4], p2[g][5], p2[g][6], p2[g][7]);
+          }
+        }
+        if (lane == 1) {
+#pragma unroll
+          for (int g = 0; g < 5; ++g) {
+            *reinterpret_cast<uint4*>(xw + 80 + g * 8) = make_uint4(p2[g][0], p2[g][1], p2[g][2], p2[g][3]);
+            *reinterpret_cast<uint4*>(xw + 80 + g * 8 + 4) = make_uint4(p2[g][4], p2[g][5], p2[g][6], p2[g][7]);
+          }
+        }
+      }
+      if (leader) bulk_wait_read<1>();            // the store issued two tiles ago has drained obuf
+      named_bar_sync(1, kEpiThreads);             // exchange rows published; obuf free
+      if (warp == 2 && lane == 0) MDC_TRACE(1, 4 * k + 1);
+      // pass 2: out[r] = P0[r] + P1[r+1] + P2[r+2], +bias, ReLU, bf16 -> staged row
+      const float* xn = xw + Cfg::kXchFloats;     // rows published by the next lane quarter
+      const bool edge = (lane >= 30) && (q < 3);
+      uint8_t* orow = obuf + (q * 32 + lane) * 160 + hf * 80;
+      uint32_t p0[2][8], p1[2][8], p2[2][8];      // two groups in flight: the loads of g + 1 fly under the math of g
+      if (!(dbg & 4)) {
+        tmem_ld8(tbase, p0[0]);
+        tmem_ld8(tbase + 80, p1[0]);
+        tmem_ld8(tbase + 160, p2[0]);
+      }
+#pragma unroll
+      for (int g = 0; g < 5; ++g) {
+        const int cur = g & 1, nxt = cur ^ 1;
+        if (!(dbg & 4)) tmem_ld_wait();
+        if (g < 4 && !(dbg & 4)) {
+          tmem_ld8(tbase + (g + 1) * 8, p0[nxt]);
+          tmem_ld8(tbase + 80 + (g + 1) * 8, p1[nxt]);
+          tmem_ld8(tbase + 160 + (g + 1) * 8, p2[nxt]);
+        }
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float a1 = __shfl_down_sync(0xffffffffu, __uint_as_float(p1[cur][e]), 1);
+          const float a2 = __shfl_down_sync(0xffffffffu, __uint_as_float(p2[cur][e]), 2);
+          v[e] = __uint_as_float(p0[cur][e]) + (lane < 31 ? a1 : 0.f) + (lane < 30 ? a2 : 0.f);
+        }
+        if (edge) {
+#pragma unroll
+          for (int e = 0; e < 8; e += 4) {
+            const int o = g * 8 + e;
+            if (lane == 30) {
+              const float4 p2a = *reinterpret_cast<const float4*>(xn + 40 + o);
+              v[e] += p2a.x; v[e + 1] += p2a.y; v[e + 2] += p2a.z; v[e + 3] += p2a.w;
+            } else {
+              const float4 p1n = *reinterpret_cast<const float4*>(xn + o);
+              const float4 p2b = *reinterpret_cast<const float4*>(xn + 80 + o);
+              v[e] += p1n.x + p2b.x; v[e + 1] += p1n.y + p2b.y; v[e + 2] += p1n.z + p2b.z; v[e + 3] += p1n.w + p2b.w;
+            }
+          }
+        }
+        const float4 ba = *reinterpret_cast<const float4*>(b2s + g * 8), bb = *reinterpret_cast<const float4*>(b2s + g * 8 + 4);
+        const uint4 o = make_uint4(cvt_relu_bf16x2(v[1] + ba.y, v[0] + ba.x), cvt_relu_bf16x2(v[3] + ba.w, v[2] + ba.z),
+                                   cvt_relu_bf16x2(v[5] + bb.y, v[4] + bb.x), cvt_relu_bf16x2(v[7] + bb.w, v[6] + bb.z));
+        *reinterpret_cast<uint4*>(orow + g * 16) = o;
+        if (g == 3) {
+          // (the loads of the last group were issued above; its wait is the next iteration's)
+        }
+      }
+      // whole buffer read: hand it back to the MMA warp
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) {
+        if (rank == 0) mbar_arrive(&tmem_empty[buf]);
+        else mbar_arrive_remote(&tmem_empty[buf], 0);
+      }
+      long long rows = Cfg::kOutRows;
+      if (row_lo + rows > total_rows) rows = total_rows - row_lo;
+      if (warp == 2 && lane == 0) MDC_TRACE(1, 4 * k + 2);
+      fence_proxy_async_smem();
+      named_bar_sync(2, kEpiThreads);
+      if (leader) {
+        if (rows > 0) bulk_s2g(act + row_lo * 80, obuf, (uint32_t)rows * 160);
+        bulk_commit();
+      }
+      if (warp == 2 && lane == 0) MDC_TRACE(1, 4 * k + 3);
+    }
+    if (leader) bulk_wait<0>();
+  } else {
+    // ================= conv1 producers: warp = (32-row block, chunk phase); fp32 FMA -> ReLU -> bf16 -> A image
+    const int pw = warp - Cfg::kProd0;
+    const int cp = pw & (Cfg::kPhases - 1);       // chunks cp, cp + kPhases, ... of every tile
+    const int row = (pw / Cfg::kPhases) * 32 + lane;
+    uint32_t k = 0, prev = 0xFFFFFFFFu;
+    for (long long base = t_first; base < num_tiles; base += t_step, ++k) {
+      const long long t0 = (base + rank) * Cfg::kOutRows;   // first tape row of this tile
+      const long long f0 = t0 / 132;
+      const long long tp = t0 + row;
+      const long long f = tp / 132;
+      const int p = (int)(tp - f * 132);
+      const bool valid = (p >= 2) && (f < n);
+      const uint32_t m = valid ? 0xFFFFFFFFu : 0u;
+      const uint32_t xb = k & 1;
+      mbar_wait(&x_full[xb], (k >> 1) & 1);
+      uint64_t xd[2][3];
+      {
+        const float* xf = reinterpret_cast<const float*>(smem + Cfg::xs + xb * (Cfg::kXF * 1024)) + (f - f0) * 256;
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            const int xi = p - 4 + j;             // conv1 position p-2 reads x[p-4 .. p-2]
+            xd[r][j] = pack_dup((valid && xi >= 0 && xi < 128) ? xf[r * 128 + xi] : 0.f);
+          }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&x_empty[xb]);
+      uint8_t* arow0 = smem + Cfg::a + row * 16;
+#ifdef MDC_VT_ABLATE
+      long long* ptrace = (blockIdx.x == 0 && pw == 0) ? trace : nullptr;
+#else
+      constexpr long long* ptrace = nullptr;
+#endif
+      static_assert(Cfg::kPhases == 2, "dispatch below");
+      if (cp == 0) conv240_produce<0>(w1c, xd, m, arow0, full, empty, k, prev, lane, rank, dbg, ptrace);
+      else conv240_produce<1>(w1c, xd, m, arow0, full, empty, k, prev, lane, rank, dbg, ptrace);
+    }
+    if (prev != 0xFFFFFFFFu) {
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        if (rank == 0) mbar_arrive(&full[prev]);
+        else mbar_arrive_remote(&full[prev], 0);
+      }
     }
   }
 
@@ -922,6 +1297,20 @@ int pack_vt_bf16(mdc_handle_s* h) {      // both tensor-core modes (MDC_MODE_BF1
               }
     if (int e = h->vt_w2_bf16.reserve(img.size() * 2)) return e;
     MDC_CUDA(cudaMemcpy(h->vt_w2_bf16.ptr, img.data(), img.size() * 2, cudaMemcpyHostToDevice));
+    // N240 image: [pair rank][chunk][group][120 accumulator columns][8 k]; column n = 120 rank + row = tap*80 + o
+    std::vector<uint16_t> img2((size_t)2 * Conv240::kBBytes / 2);
+    for (int hf = 0; hf < 2; ++hf)
+      for (int c = 0; c < Conv240::kChunks; ++c)
+        for (int g = 0; g < kGroups; ++g)
+          for (int nr = 0; nr < Conv240::kBRows; ++nr)
+            for (int e = 0; e < 8; ++e) {
+              const int ncol = hf * Conv240::kBRows + nr, j = ncol / 80, o = ncol % 80;
+              const int r = g & 1, ch = c * 16 + (g >> 1) * 8 + e;
+              img2[(((size_t)(hf * Conv240::kChunks + c) * kGroups + g) * Conv240::kBRows + nr) * 8 + e] =
+                  f2bf(w2[((size_t)(r * 3 + j) * 256 + ch) * 80 + o]);
+            }
+    if (int e = h->vt_w2_n240.reserve(img2.size() * 2)) return e;
+    MDC_CUDA(cudaMemcpy(h->vt_w2_n240.ptr, img2.data(), img2.size() * 2, cudaMemcpyHostToDevice));
   } else {
     using Cfg = ConvCfg<true>;
     std::vector<float> img((size_t)Cfg::kChunks * 2 * Cfg::kBSlot / 4);
@@ -970,6 +1359,7 @@ int pack_vt_bf16(mdc_handle_s* h) {      // both tensor-core modes (MDC_MODE_BF1
   }
   MDC_CUDA(cudaFuncSetAttribute(vt_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<false>::total));
   MDC_CUDA(cudaFuncSetAttribute(vt_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<true>::total));
+  MDC_CUDA(cudaFuncSetAttribute(vt_conv240_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv240::total));
   MDC_CUDA(cudaFuncSetAttribute(vt_dense_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DenseT32Smem::total));
   return MDC_OK;
 }
@@ -1003,6 +1393,40 @@ int launch_vt_conv(mdc_handle_s* h, const float* x, int64_t m, int64_t frame_off
   static_assert(sizeof(ConvW1) == 32 * 32 * sizeof(float), "conv1 image size");
   memcpy(&w1c, h->vt_w1_img.data(), sizeof(w1c));
   static const int dbg = getenv("MDC_VT_DEBUG") ? atoi(getenv("MDC_VT_DEBUG")) : 0;   // timing experiments
+  // MDC_VT_CONV=n240 selects the experimental second bf16 formulation (taps as N) for A/B timing: it is
+  // numerically identical but slower (2.25 ms against 1.35 ms per 65,536 frames), see DESIGN.md section 5.1
+  static const bool use_n240 = getenv("MDC_VT_CONV") && !strcmp(getenv("MDC_VT_CONV"), "n240");
+  if (!tf32 && use_n240) {
+    const long long num_tiles = (m * 132 + Conv240::kOutRows - 1) / Conv240::kOutRows;
+    const long long pairs_needed = (num_tiles + 1) / 2, pairs_max = h->num_sms / 2;
+    const unsigned grid_c = 2u * (unsigned)(pairs_needed < pairs_max ? pairs_needed : pairs_max);
+    long long* trace = nullptr;
+#ifdef MDC_VT_ABLATE
+    static long long* trace_buf = nullptr;
+    if (!trace_buf) { cudaMalloc(&trace_buf, 4 * 512 * 8); }
+    cudaMemsetAsync(trace_buf, 0, 4 * 512 * 8, stream);
+    trace = trace_buf;
+#endif
+    prof_begin(h, stream);
+    vt_conv240_kernel<<<grid_c, Conv240::kThreads, Conv240::total, stream>>>(
+        w1c, x, m, reinterpret_cast<const float*>(h->vt_b2.ptr), reinterpret_cast<const uint8_t*>(h->vt_w2_n240.ptr),
+        reinterpret_cast<__nv_bfloat16*>(act0), num_tiles, dbg, trace);
+    prof_end(h, stream);
+#ifdef MDC_VT_ABLATE
+    if (trace && getenv("MDC_VT_TRACE")) {
+      std::vector<long long> t(4 * 512);
+      cudaStreamSynchronize(stream);
+      cudaMemcpy(t.data(), trace, t.size() * 8, cudaMemcpyDeviceToHost);
+      if (FILE* f = fopen(getenv("MDC_VT_TRACE"), "w")) {
+        for (size_t i = 0; i < t.size(); ++i) fprintf(f, "%zu %lld\n", i, t[i]);
+        fclose(f);
+      }
+    }
+#endif
+    h->launches += 1;
+    MDC_CUDA(cudaGetLastError());
+    return MDC_OK;
+  }
   const long long out_rows = tf32 ? ConvCfg<true>::kOutRows : ConvCfg<false>::kOutRows;
   const long long num_st = (m * 132 + out_rows - 1) / out_rows;
   const long long pairs_needed = (num_st + 1) / 2, pairs_max = h->num_sms / 2;
