@@ -85,7 +85,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(0.05)
+            self._stop.wait(0.004)
 
     def __enter__(self):
         if self._nv:

@@ -1055,9 +1055,11 @@ vt_dense_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
 // stages.
 //
 // K = 10,560 would be a chain of 3,960 truncating accumulates (see ConvCfg), so the tensor core only
-// ever sums ONE K block: every block starts a fresh accumulator (12 MMAs) in one of two TMEM buffers,
-// and eight epilogue warps fold the finished buffer into fp32 master sums held in registers (128 per
-// thread, round-to-nearest FADD) while the MMAs of the next block fill the other buffer.
+// ever sums a RUN of two K blocks: every run starts a fresh accumulator (24 MMAs) in one of two TMEM
+// buffers, and eight epilogue warps fold the finished buffer into fp32 master sums held in registers
+// (128 per thread, round-to-nearest FADD) while the MMAs of the next run fill the other buffer.  Two
+// blocks, not one: tcgen05.ld moves 64 B/clk per SM, so folding a 128 x 256 fp32 buffer takes 2,048
+// cycles - more than the 1,536 MMA cycles of one block, less than the 3,072 of two.
 constexpr int kTM = 128;
 constexpr int kTK = 32;
 constexpr int kTStages = 2;
@@ -1065,6 +1067,9 @@ constexpr int kTKBlocks = kVtFlat / kTK;           // 330
 constexpr int kTABytes = kTM * 128;                // 16 KB
 constexpr int kTBBytes = 256 * 128;                // 32 KB
 constexpr int kTStageBytes = 2 * kTABytes + 2 * kTBBytes;
+constexpr int kTRunBlocks = 2;                     // K blocks the tensor core sums before the fold (24 MMAs)
+constexpr int kTRuns = kTKBlocks / kTRunBlocks;    // 165
+static_assert(kTKBlocks % kTRunBlocks == 0, "runs must tile K");
 constexpr int kTEpiWarps = 8;                      // (TMEM lane quarter) x (column half)
 constexpr int kDenseT32Threads = (2 + kTEpiWarps) * 32;   // TMA, MMA, 8 epilogue warps
 static_assert(kVtFlat % kTK == 0, "K must tile");
@@ -1136,29 +1141,32 @@ vt_dense_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_
     const uint32_t idesc = make_idesc_tf32(128, 256);
     const uint32_t base = smem_u32(smem);
     constexpr uint32_t hi = smem_desc_hi(1024, 2);
-    uint32_t it = 0;
+    uint32_t it = 0, run = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      for (int kb = 0; kb < kTKBlocks; ++kb, ++it) {
-        const uint32_t s = it % kTStages, ph = (it / kTStages) & 1;
-        const uint32_t buf = it & 1;
-        mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);
-        mbar_wait(&full[s], ph);
+      for (int r = 0; r < kTRuns; ++r, ++run) {
+        const uint32_t buf = run & 1;
+        mbar_wait(&acc_empty[buf], ((run >> 1) & 1) ^ 1);
         tc_fence_after_sync();
-        if (elect_one()) {
-          const uint32_t st = base + s * kTStageBytes;
-          const uint32_t ah = smem_desc_lo(st, 16), al = smem_desc_lo(st + kTABytes, 16);
-          const uint32_t bh = smem_desc_lo(st + 2 * kTABytes, 16), bl = smem_desc_lo(st + 2 * kTABytes + kTBBytes, 16);
+        for (int kk = 0; kk < kTRunBlocks; ++kk, ++it) {
+          const uint32_t s = it % kTStages, ph = (it / kTStages) & 1;
+          mbar_wait(&full[s], ph);
+          tc_fence_after_sync();
+          if (elect_one()) {
+            const uint32_t st = base + s * kTStageBytes;
+            const uint32_t ah = smem_desc_lo(st, 16), al = smem_desc_lo(st + kTABytes, 16);
+            const uint32_t bh = smem_desc_lo(st + 2 * kTABytes, 16), bl = smem_desc_lo(st + 2 * kTABytes + kTBBytes, 16);
 #pragma unroll
-          for (int ks = 0; ks < kTK / 8; ++ks) {
-            const uint32_t o = (ks * 32) >> 4;
-            mma_tf32_ss(tmem + buf * 256, desc64(al + o, hi), desc64(bh + o, hi), idesc, ks != 0);
-            mma_tf32_ss(tmem + buf * 256, desc64(ah + o, hi), desc64(bl + o, hi), idesc, 1);
-            mma_tf32_ss(tmem + buf * 256, desc64(ah + o, hi), desc64(bh + o, hi), idesc, 1);
+            for (int ks = 0; ks < kTK / 8; ++ks) {
+              const uint32_t o = (ks * 32) >> 4;
+              mma_tf32_ss(tmem + buf * 256, desc64(al + o, hi), desc64(bh + o, hi), idesc, (kk | ks) != 0);
+              mma_tf32_ss(tmem + buf * 256, desc64(ah + o, hi), desc64(bl + o, hi), idesc, 1);
+              mma_tf32_ss(tmem + buf * 256, desc64(ah + o, hi), desc64(bh + o, hi), idesc, 1);
+            }
+            mma_commit(&empty[s]);
+            if (kk == kTRunBlocks - 1) mma_commit(&acc_full[buf]);
           }
-          mma_commit(&empty[s]);
-          mma_commit(&acc_full[buf]);
+          __syncwarp();
         }
-        __syncwarp();
       }
     }
   } else {
@@ -1170,7 +1178,7 @@ vt_dense_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_
 #pragma unroll
       for (int i = 0; i < 128; ++i) acc[i] = 0.f;
 #pragma unroll 1
-      for (int kb = 0; kb < kTKBlocks; ++kb, ++it) {
+      for (int r = 0; r < kTRuns; ++r, ++it) {
         const uint32_t buf = it & 1;
         mbar_wait(&acc_full[buf], (it >> 1) & 1);
         tc_fence_after_sync();
