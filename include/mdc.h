@@ -144,6 +144,17 @@ MDC_API int mdc_fwht_i32(const int32_t* in_dev, int32_t* out_dev, int64_t n_spec
 MDC_API int mdc_fwht_i32_host(const int32_t* in_host, int32_t* out_host, int64_t n_spectra,
                               int log2_npt, int ordering, int device);
 
+/* ---- raw RTL-SDR ingest ------------------------------------------------------------------
+ * The step before the path (README.md:5: samples arrive from an RTL-SDR through the HPS; no code in
+ * the reference).  iq_dev u8 [2*n_samples]: interleaved unsigned 8-bit I0 Q0 I1 Q1 ..., centred on
+ * 127.5.  value = (u - 127.5)/128; its Q6.12 integer (2u - 255)*16 is exact.  Any subset of:
+ * frames_f32_dev  f32 [n/128,2,128]   (row 0 = I, row 1 = Q: the mdc_predict_f32 input)
+ * frames_q612_dev i32 [n/128,256]     (0-127 I, 128-255 Q: the mdc_predict_q612 input)
+ * fwht_dev        i32 [n/1024,2,1024] (Q6.12 I block then Q block: 2 rows for mdc_fwht_i32)
+ * n_samples must be a multiple of 128 (of 1024 when fwht_dev is given); NULL outputs are skipped. */
+MDC_API int mdc_sdr_ingest_u8(const uint8_t* iq_dev, int64_t n_samples, float* frames_f32_dev,
+                              int32_t* frames_q612_dev, int32_t* fwht_dev, void* stream);
+
 /* ---- caller-side epilogue --------------------------------------------------------------
  * Replaces: the confusion-matrix loops of cnn.py:200-211,239-247 / CNN.ipynb cell 12.
  * conf_dev u64 [C,C] accumulated: conf[true[i]][pred[i]] += 1.                           */

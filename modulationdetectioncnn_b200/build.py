@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmdc.so")
-SOURCES = ["mdc_api.cu", "q612.cu", "tiny_f32.cu", "fwht.cu", "vt_f32.cu", "vt_tensor.cu"]
+SOURCES = ["mdc_api.cu", "q612.cu", "tiny_f32.cu", "fwht.cu", "sdr.cu", "vt_f32.cu", "vt_tensor.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC,-fvisibility=hidden", "--use_fast_math=false",

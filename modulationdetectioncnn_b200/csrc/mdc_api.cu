@@ -521,6 +521,18 @@ int mdc_fwht_i32_host(const int32_t* in_host, int32_t* out_host, int64_t n_spect
   return rc;
 }
 
+int mdc_sdr_ingest_u8(const uint8_t* iq_dev, int64_t n_samples, float* frames_f32_dev, int32_t* frames_q612_dev,
+                      int32_t* fwht_dev, void* stream) {
+  MDC_REQUIRE(n_samples >= 0 && n_samples % 128 == 0, MDC_ERR_INVALID, "n_samples=%lld must be a multiple of 128",
+              (long long)n_samples);
+  MDC_REQUIRE(fwht_dev == nullptr || n_samples % 1024 == 0, MDC_ERR_INVALID,
+              "n_samples=%lld must be a multiple of 1024 for FWHT blocks", (long long)n_samples);
+  MDC_REQUIRE(n_samples == 0 || iq_dev != nullptr, MDC_ERR_INVALID, "iq_dev is NULL");
+  MDC_REQUIRE((((uintptr_t)iq_dev | (uintptr_t)frames_f32_dev | (uintptr_t)frames_q612_dev | (uintptr_t)fwht_dev) & 15) == 0,
+              MDC_ERR_INVALID, "buffers must be 16-byte aligned");
+  return launch_sdr_ingest(iq_dev, n_samples, frames_f32_dev, frames_q612_dev, fwht_dev, (cudaStream_t)stream);
+}
+
 int mdc_confusion_i32(const int32_t* true_dev, const int32_t* pred_dev, int64_t n, int classes,
                       unsigned long long* conf_dev, void* stream) {
   MDC_REQUIRE(classes >= 1 && classes <= kMaxClasses, MDC_ERR_UNSUPPORTED, "classes=%d", classes);

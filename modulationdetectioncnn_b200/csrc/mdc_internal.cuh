@@ -121,6 +121,8 @@ int pack_vt_f32(mdc_handle_s* h);
 int pack_vt_bf16(mdc_handle_s* h);
 int launch_fwht(const int32_t* in, int32_t* out, int64_t n, int log2_npt, int ordering,
                 cudaStream_t stream);
+int launch_sdr_ingest(const uint8_t* iq, int64_t n_samples, float* f32, int32_t* q612, int32_t* fwht,
+                      cudaStream_t stream);
 
 void prof_begin(mdc_handle_s* h, cudaStream_t s);
 void prof_end(mdc_handle_s* h, cudaStream_t s);

@@ -1,0 +1,89 @@
+// Raw RTL-SDR ingest: the step BEFORE the hot path.
+//
+// The reference only says the samples come from an RTL-SDR through the ARM/HPS side
+// (/root/reference/README.md:5); there is no code.  An RTL-SDR delivers interleaved unsigned
+// 8-bit I/Q (I0 Q0 I1 Q1 ...) centred on 127.5.  One pass over the byte stream produces every
+// input format the classifier and the spectrogram take, so the samples are read from HBM once:
+//
+//   value            = (u - 127.5) / 128                     in (-1, 1)
+//   Q6.12 integer    = (2 u - 255) * 16                      == value * 4096 exactly
+//   frames_f32   f32 [n/128][2][128]   row 0 = I, row 1 = Q   -> mdc_predict_f32
+//   frames_q612  i32 [n/128][256]      0-127 I, 128-255 Q     -> mdc_predict_q612 (test_table map, sv:88-89,102)
+//   fwht_blocks  i32 [n/1024][2][1024] Q6.12 I block, Q block -> mdc_fwht_i32 (2 spectra per block)
+//
+// HBM-bound: 2 B/sample in, 8 B/sample per requested output.  One thread per 8 samples: a 16-B
+// load, then 32-B contiguous runs per row - half a warp writes one whole 512-B frame row.
+#include "mdc_internal.cuh"
+
+namespace mdc {
+
+__device__ __forceinline__ uint4 ldg_stream_u4(const uint4* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+
+__global__ void __launch_bounds__(256)
+sdr_ingest_kernel(const uint4* __restrict__ iq, long long n_groups, float* __restrict__ f32,
+                  int* __restrict__ q612, int* __restrict__ fwht) {
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < n_groups;
+       g += (long long)gridDim.x * blockDim.x) {
+    const uint4 raw = ldg_stream_u4(iq + g);                 // samples 8 g .. 8 g + 7
+    const unsigned w[4] = {raw.x, raw.y, raw.z, raw.w};
+    int qi[8], qq[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      qi[2 * k] = (2 * (int)(w[k] & 0xFF) - 255) * 16;
+      qq[2 * k] = (2 * (int)((w[k] >> 8) & 0xFF) - 255) * 16;
+      qi[2 * k + 1] = (2 * (int)((w[k] >> 16) & 0xFF) - 255) * 16;
+      qq[2 * k + 1] = (2 * (int)(w[k] >> 24) - 255) * 16;
+    }
+    const long long frame = g >> 4;                          // 16 groups per 128-sample frame
+    const int off = (int)(g & 15) * 8;
+    if (f32) {
+      float4* di = reinterpret_cast<float4*>(f32 + frame * 256 + off);
+      float4* dq = reinterpret_cast<float4*>(f32 + frame * 256 + 128 + off);
+      constexpr float s = 1.0f / 4096.0f;                    // exact: |q| < 2^13
+      di[0] = make_float4(qi[0] * s, qi[1] * s, qi[2] * s, qi[3] * s);
+      di[1] = make_float4(qi[4] * s, qi[5] * s, qi[6] * s, qi[7] * s);
+      dq[0] = make_float4(qq[0] * s, qq[1] * s, qq[2] * s, qq[3] * s);
+      dq[1] = make_float4(qq[4] * s, qq[5] * s, qq[6] * s, qq[7] * s);
+    }
+    if (q612) {
+      int4* di = reinterpret_cast<int4*>(q612 + frame * 256 + off);
+      int4* dq = reinterpret_cast<int4*>(q612 + frame * 256 + 128 + off);
+      di[0] = make_int4(qi[0], qi[1], qi[2], qi[3]);
+      di[1] = make_int4(qi[4], qi[5], qi[6], qi[7]);
+      dq[0] = make_int4(qq[0], qq[1], qq[2], qq[3]);
+      dq[1] = make_int4(qq[4], qq[5], qq[6], qq[7]);
+    }
+    if (fwht) {
+      const long long block = g >> 7;                        // 128 groups per 1024-sample block
+      const int boff = (int)(g & 127) * 8;
+      int4* di = reinterpret_cast<int4*>(fwht + block * 2048 + boff);
+      int4* dq = reinterpret_cast<int4*>(fwht + block * 2048 + 1024 + boff);
+      di[0] = make_int4(qi[0], qi[1], qi[2], qi[3]);
+      di[1] = make_int4(qi[4], qi[5], qi[6], qi[7]);
+      dq[0] = make_int4(qq[0], qq[1], qq[2], qq[3]);
+      dq[1] = make_int4(qq[4], qq[5], qq[6], qq[7]);
+    }
+  }
+}
+
+int launch_sdr_ingest(const uint8_t* iq, int64_t n_samples, float* f32, int32_t* q612, int32_t* fwht,
+                      cudaStream_t stream) {
+  const long long groups = n_samples / 8;
+  if (groups == 0) return MDC_OK;
+  int dev = 0, sms = 148;
+  MDC_CUDA(cudaGetDevice(&dev));
+  MDC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  long long blocks = (groups + 255) / 256;
+  const long long maxb = (long long)sms * 16;
+  if (blocks > maxb) blocks = maxb;
+  sdr_ingest_kernel<<<(unsigned)blocks, 256, 0, stream>>>(reinterpret_cast<const uint4*>(iq), groups, f32, q612, fwht);
+  MDC_CUDA(cudaGetLastError());
+  return MDC_OK;
+}
+
+}  // namespace mdc

@@ -112,3 +112,22 @@ def test_full_size_properties(qsets):
     idx = torch.arange(0, n, n // 4096, device="cuda")[:4096]
     assert np.array_equal(out[idx].cpu().numpy(), sv.forward(x[idx].cpu().numpy(), *qsets["A"]))
     assert (out >= 0).all()
+
+
+def test_ten_filter_model_set_e(golden, h5w):
+    """the 10-filter integer model (DenseWeights1.txt tables + conv table quantised from
+    convmodrecnets_CNN2_0.5.wts.h5) through the same kernel family, bit-exact against the oracle."""
+    from modulationdetectioncnn_b200 import export
+    from modulationdetectioncnn_b200.qmodel import FixedPointCNN2
+    from oracle import sv_datapath as sv
+    qw = export.qweights_from_dense_dump(h5w["E_f10"], golden["qweights"]["E_dense_flat"])
+    m = FixedPointCNN2(10, 3)
+    m.set_tables(qw)
+    V = golden["vectors"]["vectors"]
+    full = philox(77).integers(-(1 << 17), 1 << 17, (2000, 256)).astype(np.int32)
+    small = np.trunc(philox(78).normal(0, 32, (4000, 256))).astype(np.int32)
+    for x in (V, full, small):
+        want = sv.forward_pre(x, qw.conv_tab, qw.dense_bias, qw.dense_tabs)
+        assert np.array_equal(m.predict(x, output="pre"), want)
+        assert np.array_equal(m.predict(x, output="argmax"), np.maximum(want, 0).argmax(-1))
+    assert int(m.class_histogram(small).sum()) == small.shape[0]
