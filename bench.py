@@ -381,7 +381,10 @@ def other_paths(torch, dev, peaks, _lib):
         lambda i: _lib.check(qm._h._lib.mdc_predict_q612(qm._h.ptr, xq.data_ptr(), n, oq.data_ptr(), None, None, hq.data_ptr(), stream)),
         lambda i: _lib.check(qm._h._lib.mdc_predict_q612_host(qm._h.ptr, xq_h.ctypes.data, nh, oq_h.ctypes.data, None, None, None)),
         1036, n, UNIT, peaks, torch, h2d=nh * 1024, d2h=nh * 12,
-        extra={"dtype": "int18/36 in int32/int64"}, host_units=nh))
+        extra={"dtype": "int18/36 in int32/int64",
+               "note": "integer-pipe-bound, not HBM-bound: 60 slice36 per lane per frame x (2 IMAD.WIDE + IMUL at 2 clk "
+                       "each on the FMA-heavy pipe) = 360 SMSP-cycles per frame -> ~3.1e9 frames/s ceiling at 1.9 GHz"},
+        host_units=nh))
     del xq, oq
 
     # C2a / C3: TinyCNN2 fp32 from the real checkpoints
@@ -399,8 +402,21 @@ def other_paths(torch, dev, peaks, _lib):
             lambda i: _lib.check(tm._h._lib.mdc_predict_f32(tm._h.ptr, xf.data_ptr(), n, pf.data_ptr(), None, None, None, stream)),
             lambda i: _lib.check(tm._h._lib.mdc_predict_f32_host(tm._h.ptr, xf_h.ctypes.data, nh, pf_h.ctypes.data, None, None, None)),
             1036, n, UNIT, peaks, torch, h2d=nh * 1024, d2h=nh * 12,
-            extra={"dtype": "f32", "flop_per_frame": flop}, host_units=nh))
+            extra={"dtype": "f32", "flop_per_frame": flop,
+                   "fp32_fma_ceiling_frames_per_s": 148 * 128 * 2 * 1.965e9 / flop}, host_units=nh))
     del xf, pf
+
+    # 8f-4: raw RTL-SDR ingest, 2^28 samples (512 MiB of u8 in, 2 GiB f32 + 2 GiB Q6.12 frames out)
+    ns = 1 << 28
+    raw = torch.randint(0, 256, (2 * ns,), generator=gen, device=dev, dtype=torch.uint8)
+    f_out = torch.empty((ns // 128, 2, 128), dtype=torch.float32, device=dev)
+    q_out = torch.empty((ns // 128, 256), dtype=torch.int32, device=dev)
+    lib0 = _lib.load()
+    out.append(hbm_path(
+        "sdr_ingest u8 -> f32 + Q6.12 frames (8f-4)", None,
+        lambda i: _lib.check(lib0.mdc_sdr_ingest_u8(raw.data_ptr(), ns, f_out.data_ptr(), q_out.data_ptr(), None, stream)),
+        None, 256 + 1024 + 1024, ns // 128, UNIT, peaks, torch, extra={"dtype": "u8 -> f32 / int32"}))
+    del raw, f_out, q_out
 
     # C4: FWHT 1024-pt, 2^18 spectra (1 GiB in + 1 GiB out)
     s = 1 << 18

@@ -33,6 +33,8 @@ def ingest_u8(iq, want: Sequence[str] = ("f32",)) -> Dict[str, object]:
     if iq.numel() % 2:
         raise ValueError("odd number of bytes: I/Q pairs expected")
     n = iq.numel() // 2
+    if n % 128 or ("fwht" in want and n % 1024):
+        raise ValueError(f"{n} samples: frames need a multiple of 128, FWHT blocks a multiple of 1024")
     out: Dict[str, object] = {}
     with torch.cuda.device(iq.device):
         if "f32" in want:

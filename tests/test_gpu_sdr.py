@@ -58,10 +58,15 @@ def test_ingest_feeds_predict_and_fwht(golden, qsets, h5w):
 def test_ingest_rejects_bad_sizes():
     import torch
     from modulationdetectioncnn_b200 import _lib, sdr
-    with pytest.raises(_lib.MdcError):
+    with pytest.raises(ValueError):
         sdr.ingest_u8(torch.zeros(2 * 100, dtype=torch.uint8, device="cuda"), ("f32",))
-    with pytest.raises(_lib.MdcError):
+    with pytest.raises(ValueError):
         sdr.ingest_u8(torch.zeros(2 * 128, dtype=torch.uint8, device="cuda"), ("fwht",))
+    buf = torch.zeros(4096, dtype=torch.uint8, device="cuda")
+    lib = _lib.load()
+    assert lib.mdc_sdr_ingest_u8(buf.data_ptr(), 100, buf.data_ptr(), None, None, None) != 0        # C ABI checks too
+    assert lib.mdc_sdr_ingest_u8(buf.data_ptr(), 128, None, None, buf.data_ptr(), None) != 0
+    assert b"1024" in lib.mdc_last_error()
     with pytest.raises(ValueError):
         sdr.ingest_u8(np.zeros(256, np.uint8), ("f32",))
     assert sdr.ingest_u8(torch.zeros(0, dtype=torch.uint8, device="cuda"), ("f32",))["f32"].shape == (0, 2, 128)
