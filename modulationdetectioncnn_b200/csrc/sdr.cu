@@ -45,28 +45,28 @@ sdr_ingest_kernel(const uint4* __restrict__ iq, long long n_groups, float* __res
       float4* di = reinterpret_cast<float4*>(f32 + frame * 256 + off);
       float4* dq = reinterpret_cast<float4*>(f32 + frame * 256 + 128 + off);
       constexpr float s = 1.0f / 4096.0f;                    // exact: |q| < 2^13
-      di[0] = make_float4(qi[0] * s, qi[1] * s, qi[2] * s, qi[3] * s);
-      di[1] = make_float4(qi[4] * s, qi[5] * s, qi[6] * s, qi[7] * s);
-      dq[0] = make_float4(qq[0] * s, qq[1] * s, qq[2] * s, qq[3] * s);
-      dq[1] = make_float4(qq[4] * s, qq[5] * s, qq[6] * s, qq[7] * s);
+      __stcs(di + 0, make_float4(qi[0] * s, qi[1] * s, qi[2] * s, qi[3] * s));
+      __stcs(di + 1, make_float4(qi[4] * s, qi[5] * s, qi[6] * s, qi[7] * s));
+      __stcs(dq + 0, make_float4(qq[0] * s, qq[1] * s, qq[2] * s, qq[3] * s));
+      __stcs(dq + 1, make_float4(qq[4] * s, qq[5] * s, qq[6] * s, qq[7] * s));
     }
     if (q612) {
       int4* di = reinterpret_cast<int4*>(q612 + frame * 256 + off);
       int4* dq = reinterpret_cast<int4*>(q612 + frame * 256 + 128 + off);
-      di[0] = make_int4(qi[0], qi[1], qi[2], qi[3]);
-      di[1] = make_int4(qi[4], qi[5], qi[6], qi[7]);
-      dq[0] = make_int4(qq[0], qq[1], qq[2], qq[3]);
-      dq[1] = make_int4(qq[4], qq[5], qq[6], qq[7]);
+      __stcs(di + 0, make_int4(qi[0], qi[1], qi[2], qi[3]));
+      __stcs(di + 1, make_int4(qi[4], qi[5], qi[6], qi[7]));
+      __stcs(dq + 0, make_int4(qq[0], qq[1], qq[2], qq[3]));
+      __stcs(dq + 1, make_int4(qq[4], qq[5], qq[6], qq[7]));
     }
     if (fwht) {
       const long long block = g >> 7;                        // 128 groups per 1024-sample block
       const int boff = (int)(g & 127) * 8;
       int4* di = reinterpret_cast<int4*>(fwht + block * 2048 + boff);
       int4* dq = reinterpret_cast<int4*>(fwht + block * 2048 + 1024 + boff);
-      di[0] = make_int4(qi[0], qi[1], qi[2], qi[3]);
-      di[1] = make_int4(qi[4], qi[5], qi[6], qi[7]);
-      dq[0] = make_int4(qq[0], qq[1], qq[2], qq[3]);
-      dq[1] = make_int4(qq[4], qq[5], qq[6], qq[7]);
+      __stcs(di + 0, make_int4(qi[0], qi[1], qi[2], qi[3]));
+      __stcs(di + 1, make_int4(qi[4], qi[5], qi[6], qi[7]));
+      __stcs(dq + 0, make_int4(qq[0], qq[1], qq[2], qq[3]));
+      __stcs(dq + 1, make_int4(qq[4], qq[5], qq[6], qq[7]));
     }
   }
 }

@@ -385,17 +385,26 @@ vt_conv_kernel(const __grid_constant__ ConvW1 w1c, const float* __restrict__ x, 
           continue;
         }
         uint8_t* orow = obuf + (q * 32 + lane) * 160;
+        uint4 o[10];
 #pragma unroll
         for (int c8 = 0; c8 < 10; ++c8) {
-          if (dbg & 4) break;
           const float4 ba = b2s[2 * c8], bb = b2s[2 * c8 + 1];
           const uint32_t* vv = &v[c8 * 8];
-          const uint4 o = make_uint4(
+          o[c8] = make_uint4(
               cvt_relu_bf16x2(__uint_as_float(vv[1]) + ba.y, __uint_as_float(vv[0]) + ba.x),
               cvt_relu_bf16x2(__uint_as_float(vv[3]) + ba.w, __uint_as_float(vv[2]) + ba.z),
               cvt_relu_bf16x2(__uint_as_float(vv[5]) + bb.y, __uint_as_float(vv[4]) + bb.x),
               cvt_relu_bf16x2(__uint_as_float(vv[7]) + bb.w, __uint_as_float(vv[6]) + bb.z));
-          *reinterpret_cast<uint4*>(orow + c8 * 16) = o;
+        }
+        // rows are 160 B apart, so the 16-B chunks of lanes l and l + 4 fall into the same banks: lanes with
+        // bit 2 set store their chunks rotated by one, which makes every quarter-warp store conflict-free
+        const bool rot = (lane & 4) != 0;
+#pragma unroll
+        for (int j = 0; j < 10; ++j) {
+          if (dbg & 4) break;
+          const uint4 a = o[j], b = o[(j + 1) % 10];
+          const uint4 val = make_uint4(rot ? b.x : a.x, rot ? b.y : a.y, rot ? b.z : a.z, rot ? b.w : a.w);
+          *reinterpret_cast<uint4*>(orow + (rot ? ((j + 1) % 10) : j) * 16) = val;
         }
         fence_proxy_async_smem();
         named_bar_sync(2, 128);
