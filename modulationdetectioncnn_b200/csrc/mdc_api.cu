@@ -1,6 +1,7 @@
 // C-ABI entry points of libmdc.so (see include/mdc.h) and the host-buffer pipeline.
 #include <string.h>
 
+#include <algorithm>
 #include <mutex>
 
 #include "mdc_internal.cuh"
@@ -388,6 +389,27 @@ int mdc_set_weights_q612(mdc_handle_t h, const int32_t* conv_tab, const int32_t*
         for (int s = 0; s < 128; ++s)
           img[(((size_t)f * C + c) * 2 + iq) * 128 + s] =
               8 * dense_tabs[(size_t)(2 * c + iq) * tab + 128 * f + (s > 0 ? s - 1 : 0)];
+  // Input bound for the kernel's 32-bit path.  With |x| <= X: conv sums |m| <= X*csum, so |m| < 2^28 needs
+  // X <= (2^28-1)/csum; then |slice| <= X*csum/4096 + 1 and, as long as that plus the largest |bias| stays below
+  // ylim <= 2^16-2, the bias add cannot wrap and every conv output obeys y <= ylim, where ylim = (2^28-1)/dsum
+  // keeps the dense sums |yI*wI + yQ*wQ| <= ylim*dsum < 2^28 too.
+  {
+    long long csum = 0, bmax = 0, dsum = 0;
+    for (int f = 0; f < F; ++f) {
+      csum = std::max(csum, (long long)std::abs(conv_tab[3 * f]) + std::abs(conv_tab[3 * f + 1]));
+      bmax = std::max(bmax, (long long)std::abs(conv_tab[3 * f + 2]));
+    }
+    for (int c = 0; c < C; ++c)
+      for (size_t a = 0; a < tab; ++a)
+        dsum = std::max(dsum, (long long)std::abs(dense_tabs[(size_t)(2 * c) * tab + a]) + std::abs(dense_tabs[(size_t)(2 * c + 1) * tab + a]));
+    const long long lim = (1ll << 28) - 1, top = (1ll << 17) - 1;
+    const long long xlim = csum ? lim / csum : top;
+    // (2^16 - 2: the conv bias is folded into the 32-bit accumulator as bias * 2^15, see conv18_sel)
+    const long long ylim = std::min(dsum ? lim / dsum : top, (1ll << 16) - 2);
+    long long xfast = -1;
+    if (ylim > bmax + 1) xfast = std::min(xlim, csum ? ((ylim - bmax - 1) * 4096) / csum : top);
+    h->q_xfast = (int)std::min(xfast, 1ll << 17);
+  }
   if (int e = h->q_dense.reserve(img.size() * sizeof(int))) return e;
   MDC_CUDA(cudaMemcpy(h->q_dense.ptr, img.data(), img.size() * sizeof(int), cudaMemcpyHostToDevice));
   h->have_q = true;

@@ -93,6 +93,7 @@ struct mdc_handle_s {
   bool have_q = false;
   std::vector<int> q_conv_host, q_bias_host;
   mdc::DeviceBuffer q_dense;    // pre-skewed [f][c][iq][128]
+  int q_xfast = -1;             // input bound under which every 36-bit sum provably fits 29 bits (q612.cu)
 
   // ---- host pipeline (lazy)
   mdc::HostPipe* pipe = nullptr;

@@ -22,6 +22,7 @@ struct QParams {
   int conv[3 * kMaxFilters];
   int bias[kMaxClasses];
   int F, C;
+  int xfast;   // frames with max |x| <= xfast take the 32-bit path (-1: never), see slice_small()
 };
 
 __device__ __forceinline__ int wrap18(int v) {   // sign-extend bit 17 (SGXT)
@@ -53,6 +54,55 @@ __device__ __forceinline__ int conv18(int a, int w0, int c, int w1, int bias) {
   return o < 0 ? 0 : o;
 }
 
+// The same slice when the host has PROVEN |m| < 2^28 for this frame (launch_q612 derives the input bound
+// from the ROM contents): then m[35] = m[28] = sign(m), {m[35], m[28:12]} = floor(m / 4096), 8 m fits 32
+// bits and two IMAD plus one arithmetic shift do it - 3 instructions instead of 5, one ALU-pipe op
+// instead of two (the ALU pipe is the kernel's busiest).  Bit-identical to slice36 on that domain.
+__device__ __forceinline__ int slice_small(int a, int b8, int c, int d8) { return (a * b8 + c * d8) >> 15; }
+
+template <bool FAST>
+__device__ __forceinline__ int slice_sel(int a, int b8, int c, int d8) {
+  return FAST ? slice_small(a, b8, c, d8) : slice36(a, b8, c, d8);
+}
+// conv MAC + bias + ReLU.  On the small-signal path the host bound also guarantees |slice + bias| < 2^16, so
+// the 18-bit wrap is the identity and the bias rides in the accumulator: floor((8 m + bias 2^15) / 2^15).
+template <bool FAST>
+__device__ __forceinline__ int conv18_sel(int a, int w0, int c, int w1, int bias) {
+  int o = FAST ? ((a * w0 + (c * w1 + (bias << 15))) >> 15) : wrap18(slice36(a, w0, c, w1) + bias);
+  return o < 0 ? 0 : o;
+}
+
+// class sums of one frame (lane = 4 sample positions of both rows)
+template <int F, int C, bool WREG, bool FAST>
+__device__ __forceinline__ void frame_sums(const QParams& p, const int4* __restrict__ dense4, const int4 (&w)[WREG ? F * C * 2 : 1],
+                                           const int (&I)[5], const int (&Q)[5], int lane, unsigned (&acc)[C]) {
+#pragma unroll
+  for (int c = 0; c < C; ++c) acc[c] = 0u;
+#pragma unroll
+  for (int k = 0; k < F; ++k) {
+    const int w0 = p.conv[3 * k], w1 = p.conv[3 * k + 1], b = p.conv[3 * k + 2];
+    int yi[4], yq[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      yi[i] = conv18_sel<FAST>(I[i], w0, I[i + 1], w1, b);
+      yq[i] = conv18_sel<FAST>(Q[i], w0, Q[i + 1], w1, b);
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      int4 wi, wq;
+      if (WREG) {
+        wi = w[(k * C + c) * 2];
+        wq = w[(k * C + c) * 2 + 1];
+      } else {
+        wi = __ldg(dense4 + ((k * C + c) * 2) * 32 + lane);
+        wq = __ldg(dense4 + ((k * C + c) * 2 + 1) * 32 + lane);
+      }
+      acc[c] += (unsigned)slice_sel<FAST>(yi[0], wi.x, yq[0], wq.x) + (unsigned)slice_sel<FAST>(yi[1], wi.y, yq[1], wq.y) +
+                (unsigned)slice_sel<FAST>(yi[2], wi.z, yq[2], wq.z) + (unsigned)slice_sel<FAST>(yi[3], wi.w, yq[3], wq.w);
+    }
+  }
+}
+
 __device__ __forceinline__ int4 ldg_stream(const int4* p) {
   int4 r;
   asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
@@ -61,8 +111,8 @@ __device__ __forceinline__ int4 ldg_stream(const int4* p) {
 }
 
 // dense image: [f][c][iq][128] with entry s = tab[2c+iq][128 f + max(s-1,0)]  (pre-skewed on host)
-template <int F, int C, bool WREG>
-__global__ void __launch_bounds__(256, 2)
+template <int F, int C, bool WREG, int MINB>
+__global__ void __launch_bounds__(256, MINB)
 q612_kernel(const QParams p, const int4* __restrict__ dense4, const int4* __restrict__ x,
             long long n, int* __restrict__ out, int* __restrict__ pre, int* __restrict__ cls,
             unsigned long long* __restrict__ hist) {
@@ -86,7 +136,8 @@ q612_kernel(const QParams p, const int4* __restrict__ dense4, const int4* __rest
   while (f < n) {
     const long long fn = f + nwarps;
     int4 ni = xi, nq = xq;
-    if (fn < n) {  // prefetch the next frame of this warp
+    if (fn < n) {  // prefetch the next frame of this warp (a second frame in flight measured slower: the kernel is
+                   // issue-bound, not latency-bound)
       ni = ldg_stream(x + fn * 64 + lane);
       nq = ldg_stream(x + fn * 64 + 32 + lane);
     }
@@ -98,30 +149,13 @@ q612_kernel(const QParams p, const int4* __restrict__ dense4, const int4* __rest
     if (lane == 0) { I[0] = 0; Q[0] = 0; }   // zero padding: ad_in_data[0] (sv:485)
 
     unsigned acc[C];   // unsigned: wrap-around mod 2^32 is defined behaviour
-#pragma unroll
-    for (int c = 0; c < C; ++c) acc[c] = 0u;
-#pragma unroll
-    for (int k = 0; k < F; ++k) {
-      const int w0 = p.conv[3 * k], w1 = p.conv[3 * k + 1], b = p.conv[3 * k + 2];
-      int yi[4], yq[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        yi[i] = conv18(I[i], w0, I[i + 1], w1, b);
-        yq[i] = conv18(Q[i], w0, Q[i + 1], w1, b);
-      }
-#pragma unroll
-      for (int c = 0; c < C; ++c) {
-        int4 wi, wq;
-        if (WREG) {
-          wi = w[(k * C + c) * 2];
-          wq = w[(k * C + c) * 2 + 1];
-        } else {
-          wi = __ldg(dense4 + ((k * C + c) * 2) * 32 + lane);
-          wq = __ldg(dense4 + ((k * C + c) * 2 + 1) * 32 + lane);
-        }
-        acc[c] += (unsigned)slice36(yi[0], wi.x, yq[0], wq.x) + (unsigned)slice36(yi[1], wi.y, yq[1], wq.y) +
-                  (unsigned)slice36(yi[2], wi.z, yq[2], wq.z) + (unsigned)slice36(yi[3], wi.w, yq[3], wq.w);
-      }
+    {
+      // largest |x| of the frame decides (warp-uniformly) between the 32-bit and the 36-bit arithmetic
+      int ax = max(max(abs(I[1]), abs(I[2])), max(abs(I[3]), abs(I[4])));
+      ax = max(ax, max(max(abs(Q[1]), abs(Q[2])), max(abs(Q[3]), abs(Q[4]))));
+      const int xmax = __reduce_max_sync(0xffffffffu, ax);
+      if (xmax <= p.xfast) frame_sums<F, C, WREG, true>(p, dense4, w, I, Q, lane, acc);
+      else frame_sums<F, C, WREG, false>(p, dense4, w, I, Q, lane, acc);
     }
     int best = 0, bestv = 0;
 #pragma unroll
@@ -211,16 +245,20 @@ int launch_q612(mdc_handle_s* h, const int32_t* x, int64_t n, int32_t* out, int3
   for (int i = 0; i < kMaxClasses; ++i) p.bias[i] = i < h->C ? bias[i] : 0;
   p.F = h->F;
   p.C = h->C;
+  p.xfast = h->q_xfast;
   const int threads = 256;
   long long warps_needed = n;
-  long long max_blocks = (long long)h->num_sms * 2 * 4;   // 4 waves of 2 resident CTAs per SM
+  // MDC_Q612_VARIANT (tuning aid): 0 = ROM rows in registers, 2 CTAs/SM; 1 = ROM rows through L1, 4 CTAs/SM
+  static const int variant = getenv("MDC_Q612_VARIANT") ? atoi(getenv("MDC_Q612_VARIANT")) : 0;
+  long long max_blocks = (long long)h->num_sms * (variant ? 4 : 2) * 4;   // 4 waves of resident CTAs
   long long blocks = (warps_needed * 32 + threads - 1) / threads;
   if (blocks > max_blocks) blocks = max_blocks;
   const int4* d4 = reinterpret_cast<const int4*>(h->q_dense.ptr);
   const int4* x4 = reinterpret_cast<const int4*>(x);
   prof_begin(h, stream);
   if (h->F == 3 && h->C == 3) {
-    q612_kernel<3, 3, true><<<(unsigned)blocks, threads, 0, stream>>>(p, d4, x4, n, out, pre, cls, hist);
+    if (variant) q612_kernel<3, 3, false, 4><<<(unsigned)blocks, threads, 0, stream>>>(p, d4, x4, n, out, pre, cls, hist);
+    else q612_kernel<3, 3, true, 2><<<(unsigned)blocks, threads, 0, stream>>>(p, d4, x4, n, out, pre, cls, hist);
   } else {
     q612_generic_kernel<<<(unsigned)blocks, threads, 0, stream>>>(p, d4, x4, n, out, pre, cls, hist);
   }

@@ -131,3 +131,32 @@ def test_ten_filter_model_set_e(golden, h5w):
         assert np.array_equal(m.predict(x, output="pre"), want)
         assert np.array_equal(m.predict(x, output="argmax"), np.maximum(want, 0).argmax(-1))
     assert int(m.class_histogram(small).sum()) == small.shape[0]
+
+
+def _xfast(conv_tab, dense_tabs):
+    """The input bound of the kernel's 32-bit path, derived as in mdc_set_weights_q612 (mdc_api.cu)."""
+    w = np.abs(conv_tab.astype(np.int64)).reshape(-1, 3)
+    csum, bmax = int((w[:, 0] + w[:, 1]).max()), int(w[:, 2].max())
+    d = np.abs(dense_tabs.astype(np.int64)).reshape(dense_tabs.shape[0] // 2, 2, -1)
+    dsum = int((d[:, 0] + d[:, 1]).max())
+    lim, top = (1 << 28) - 1, (1 << 17) - 1
+    xlim = lim // csum if csum else top
+    ylim = min(lim // dsum if dsum else top, (1 << 16) - 2)
+    return min(xlim, ((ylim - bmax - 1) * 4096) // csum if csum else top) if ylim > bmax + 1 else -1
+
+
+@pytest.mark.parametrize("k", list("ABC"))
+def test_small_signal_path_is_exact_up_to_its_bound(qsets, k):
+    """Frames whose largest |x| is within the host-derived bound use 32-bit sums; frames just above it use the
+    36-bit slices.  Both sides of the bound, with every sample AT the bound, must equal the oracle."""
+    from oracle import sv_datapath as sv
+    ct, db, dt = qsets[k]
+    xf = _xfast(ct, dt)
+    assert xf > 200, xf                                  # the shipped ROMs do have a small-signal regime
+    m = _model(qsets, k)
+    g = philox(31)
+    for bound in (xf, xf + 1, xf // 2):
+        x = g.integers(-bound, bound + 1, (3000, 256)).astype(np.int32)
+        x[:500] = np.where(g.random((500, 256)) < 0.5, -bound, bound)      # all samples at the extreme
+        x[500:1000, ::7] = bound
+        assert np.array_equal(m.predict(x, output="pre"), sv.forward_pre(x, ct, db, dt)), (k, bound)
