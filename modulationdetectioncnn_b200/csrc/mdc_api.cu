@@ -224,9 +224,11 @@ static int run_vt_host_pipeline(mdc_handle_s* h, const float* x, int64_t n, floa
   for (int64_t p0 = 0; p0 < n; p0 += pass, ++pi) {
     const int64_t pm = (n - p0) < pass ? (n - p0) : pass;
     const int ob = (int)(pi & 1);
-    for (int64_t c0 = 0; c0 < pm; c0 += chunk, ++i) {
+    for (int64_t c0 = 0, step = 0; c0 < pm; c0 += step, ++i) {
       const int k = (int)(i % S);
-      const int64_t m = (pm - c0) < chunk ? (pm - c0) : chunk;
+      // the very first chunk is small (2 MiB): nothing can overlap its copy
+      step = (p0 == 0 && c0 == 0 && chunk == 8192 && pm > 2 * chunk) ? 2048 : chunk;
+      const int64_t m = (pm - c0) < step ? (pm - c0) : step;
       if (i >= S) MDC_CUDA(cudaStreamWaitEvent(P.s_h2d, P.e_comp[k], 0));
       MDC_CUDA(cudaMemcpyAsync(P.x[k].ptr, x + (p0 + c0) * kFrameElems, (size_t)m * kFrameElems * sizeof(float),
                                cudaMemcpyHostToDevice, P.s_h2d));
