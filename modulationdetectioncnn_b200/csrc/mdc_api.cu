@@ -208,8 +208,15 @@ static int run_vt_host_pipeline(mdc_handle_s* h, const float* x, int64_t n, floa
   if (int e = P.init()) return e;
   const int C = h->C;
   constexpr int S = HostPipe::kSlots;
-  const int64_t pass = vt_pass_frames(h);
-  const int64_t chunk = h->mode == MDC_MODE_TF32X3 ? pass : 8192;
+  // bf16: passes of 32,768 frames (128 dense tiles, one wave): dense1 of the first half runs under the second
+  // half's copies and convolutions, so only half a pass of dense work is left after the last byte has arrived.
+  // (MDC_VT_PASS / MDC_VT_CHUNK / MDC_VT_FIRST: tuning aids)
+  static const int64_t env_pass = getenv("MDC_VT_PASS") ? atoll(getenv("MDC_VT_PASS")) : 32768;
+  static const int64_t env_chunk = getenv("MDC_VT_CHUNK") ? atoll(getenv("MDC_VT_CHUNK")) : 8192;
+  static const int64_t env_first = getenv("MDC_VT_FIRST") ? atoll(getenv("MDC_VT_FIRST")) : 2048;
+  const bool tf32 = h->mode == MDC_MODE_TF32X3;
+  const int64_t pass = tf32 ? vt_pass_frames(h) : env_pass;
+  const int64_t chunk = tf32 ? pass : (env_chunk < pass ? env_chunk : pass);
   const int64_t cap = n < pass ? n : pass;
   if (int e = vt_reserve(h, cap)) return e;
   if (hist) MDC_CUDA(cudaMemsetAsync(P.hist.ptr, 0, C * sizeof(unsigned long long), P.s_comp));
@@ -227,7 +234,7 @@ static int run_vt_host_pipeline(mdc_handle_s* h, const float* x, int64_t n, floa
     for (int64_t c0 = 0, step = 0; c0 < pm; c0 += step, ++i) {
       const int k = (int)(i % S);
       // the very first chunk is small (2 MiB): nothing can overlap its copy
-      step = (p0 == 0 && c0 == 0 && chunk == 8192 && pm > 2 * chunk) ? 2048 : chunk;
+      step = (p0 == 0 && c0 == 0 && !tf32 && pm > 2 * env_first) ? env_first : chunk;
       const int64_t m = (pm - c0) < step ? (pm - c0) : step;
       if (i >= S) MDC_CUDA(cudaStreamWaitEvent(P.s_h2d, P.e_comp[k], 0));
       MDC_CUDA(cudaMemcpyAsync(P.x[k].ptr, x + (p0 + c0) * kFrameElems, (size_t)m * kFrameElems * sizeof(float),

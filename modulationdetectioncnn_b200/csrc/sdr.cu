@@ -78,8 +78,9 @@ int launch_sdr_ingest(const uint8_t* iq, int64_t n_samples, float* f32, int32_t*
   int dev = 0, sms = 148;
   MDC_CUDA(cudaGetDevice(&dev));
   MDC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  static const int bpsm = getenv("MDC_SDR_BLOCKS_PER_SM") ? atoi(getenv("MDC_SDR_BLOCKS_PER_SM")) : 64;   // tuning aid (measured: 4 -> 4.09, 16 -> 4.22, 64 -> 4.48 TB/s)
   long long blocks = (groups + 255) / 256;
-  const long long maxb = (long long)sms * 16;
+  const long long maxb = (long long)sms * bpsm;
   if (blocks > maxb) blocks = maxb;
   sdr_ingest_kernel<<<(unsigned)blocks, 256, 0, stream>>>(reinterpret_cast<const uint4*>(iq), groups, f32, q612, fwht);
   MDC_CUDA(cudaGetLastError());
