@@ -176,8 +176,10 @@ MDC_API int mdc_profile_read(mdc_handle_t h, double* ms_total, int64_t* launches
 
 /* diagnostics: copy an intermediate of the handle's LAST predict pass to the host (synchronises
  * the device).  what = 0: VT-CNN2 conv2 activations (bf16 [frames*132][80] in BF16 mode, f32 in
- * FP32 mode) - `model3`-style layer taps of CNN.ipynb cell 17; what = 1: dense1 activations
- * f32 [frames][256].  bytes is clamped to the workspace size; returns the bytes copied in *copied. */
+ * FP32 mode, f32 hi matrix then lo matrix in TF32X3 mode) - `model3`-style layer taps of CNN.ipynb cell 17;
+ * what = 1: dense1 activations f32 [frames][256] (BF16 mode fuses the rest of the network into the dense1
+ * kernel and keeps no copy unless the process runs with MDC_VT_KEEP_H=1).  bytes is clamped to the workspace
+ * size; returns the bytes copied in *copied. */
 MDC_API int mdc_debug_read(mdc_handle_t h, int what, void* host_dst, size_t bytes, size_t* copied);
 
 #ifdef __cplusplus
