@@ -160,6 +160,12 @@ MDC_API int mdc_sdr_ingest_u8(const uint8_t* iq_dev, int64_t n_samples, float* f
  * conf_dev u64 [C,C] accumulated: conf[true[i]][pred[i]] += 1.                           */
 MDC_API int mdc_confusion_i32(const int32_t* true_dev, const int32_t* pred_dev, int64_t n,
                               int classes, unsigned long long* conf_dev, void* stream);
+/* One matrix per group in a single pass - replaces the per-SNR loop of cnn.py:227-255 (select the
+ * frames of one SNR, predict, count, accuracy = trace / sum).  group_dev i32 [n] in [0, groups)
+ * (NULL = one group); conf_dev u64 [groups,C,C] accumulated.  Out-of-range labels are skipped.  */
+MDC_API int mdc_confusion_grouped_i32(const int32_t* true_dev, const int32_t* pred_dev,
+                                      const int32_t* group_dev, int64_t n, int classes, int groups,
+                                      unsigned long long* conf_dev, void* stream);
 
 /* ---- introspection ---------------------------------------------------------------------*/
 MDC_API const char* mdc_last_error(void);

@@ -401,22 +401,31 @@ static int run_vt_host_streaming(mdc_handle_s* h, const float* x, int64_t n, flo
   return MDC_OK;
 }
 
-// ---- confusion matrix ------------------------------------------------------------------
-__global__ void confusion_kernel(const int* __restrict__ t, const int* __restrict__ p, long long n, int C,
-                                 unsigned long long* __restrict__ conf) {
-  __shared__ unsigned int sm[kMaxClasses * kMaxClasses];
-  for (int i = threadIdx.x; i < C * C; i += blockDim.x) sm[i] = 0;
-  __syncthreads();
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const int a = t[i], b = p[i];
-    if (a >= 0 && a < C && b >= 0 && b < C) atomicAdd(&sm[a * C + b], 1u);
+// ---- confusion matrix (optionally one per group, e.g. per SNR) -----------------------------
+// conf[g][t][p] += 1 for every frame; counters are block-local in shared memory when they fit, then added
+// to the global matrix with one atomic per non-zero cell.
+__global__ void confusion_kernel(const int* __restrict__ t, const int* __restrict__ p, const int* __restrict__ grp,
+                                 long long n, int C, int G, int use_smem, unsigned long long* __restrict__ conf) {
+  extern __shared__ unsigned int sm[];
+  const int cells = G * C * C;
+  if (use_smem) {
+    for (int i = threadIdx.x; i < cells; i += blockDim.x) sm[i] = 0;
+    __syncthreads();
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < C * C; i += blockDim.x)
-    if (sm[i]) atomicAdd(conf + i, (unsigned long long)sm[i]);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int a = t[i], b = p[i], g = grp ? grp[i] : 0;
+    if (a >= 0 && a < C && b >= 0 && b < C && g >= 0 && g < G) {
+      const int cell = (g * C + a) * C + b;
+      if (use_smem) atomicAdd(&sm[cell], 1u);
+      else atomicAdd(conf + cell, 1ull);
+    }
+  }
+  if (use_smem) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < cells; i += blockDim.x)
+      if (sm[i]) atomicAdd(conf + i, (unsigned long long)sm[i]);
+  }
 }
-
-
 
 #define MDC_CHECK_HANDLE(h)                                                   \
   MDC_REQUIRE((h) != nullptr, MDC_ERR_INVALID, "null handle");                \
@@ -706,17 +715,26 @@ int mdc_sdr_ingest_u8(const uint8_t* iq_dev, int64_t n_samples, float* frames_f3
   return launch_sdr_ingest(iq_dev, n_samples, frames_f32_dev, frames_q612_dev, fwht_dev, (cudaStream_t)stream);
 }
 
-int mdc_confusion_i32(const int32_t* true_dev, const int32_t* pred_dev, int64_t n, int classes,
-                      unsigned long long* conf_dev, void* stream) {
+int mdc_confusion_grouped_i32(const int32_t* true_dev, const int32_t* pred_dev, const int32_t* group_dev, int64_t n,
+                              int classes, int groups, unsigned long long* conf_dev, void* stream) {
   MDC_REQUIRE(classes >= 1 && classes <= kMaxClasses, MDC_ERR_UNSUPPORTED, "classes=%d", classes);
+  MDC_REQUIRE(groups >= 1 && groups <= 4096, MDC_ERR_UNSUPPORTED, "groups=%d outside 1..4096", groups);
   MDC_REQUIRE(n >= 0 && (n == 0 || (true_dev && pred_dev && conf_dev)), MDC_ERR_INVALID, "bad arguments");
   if (n == 0) return MDC_OK;
-  // at most 2^22 increments of a 32-bit shared counter per block
+  const int cells = groups * classes * classes;
+  const int use_smem = cells <= 8192;                   // 32 KB of 32-bit block-local counters
+  // at most 2^20 increments of a 32-bit shared counter per block
   long long blocks = (n + 256LL * 4096 - 1) / (256LL * 4096);
   if (blocks < 148) blocks = n < 148 * 256 ? 1 : 148;
-  confusion_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(true_dev, pred_dev, n, classes, conf_dev);
+  confusion_kernel<<<(unsigned)blocks, 256, use_smem ? cells * sizeof(unsigned) : 0, (cudaStream_t)stream>>>(
+      true_dev, pred_dev, group_dev, n, classes, groups, use_smem, conf_dev);
   MDC_CUDA(cudaGetLastError());
   return MDC_OK;
+}
+
+int mdc_confusion_i32(const int32_t* true_dev, const int32_t* pred_dev, int64_t n, int classes,
+                      unsigned long long* conf_dev, void* stream) {
+  return mdc_confusion_grouped_i32(true_dev, pred_dev, nullptr, n, classes, 1, conf_dev, stream);
 }
 
 // ---- introspection ---------------------------------------------------------------------
