@@ -1079,7 +1079,9 @@ vt_dense_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
 // dense1 in 3xTF32: h = relu(act W3 + b3) with act = act_hi + act_lo, W3 = W3_hi + W3_lo (fp32 words,
 // tf32 hi/lo split), three kind::tf32 MMAs per K step.  128 frames x 256 outputs per tile, K blocks
 // of 32 values (128-B swizzled rows); 96 KB per stage (A hi/lo 16 KB each, B hi/lo 32 KB each), two
-// stages.
+// stages.  CTAs run in clusters of two that walk the K blocks in lockstep on different frame tiles: each loads
+// HALF of every W3 block and multicasts it into both CTAs' stages, which halves the L2 traffic of re-streaming
+// the 21.6 MB of W3 hi/lo per tile (the kernel was L2-bound on exactly that).
 //
 // K = 10,560 would be a chain of 3,960 truncating accumulates (see ConvCfg), so the tensor core only
 // ever sums a RUN of two K blocks: every run starts a fresh accumulator (24 MMAs) in one of two TMEM
@@ -1111,7 +1113,7 @@ struct DenseT32Smem {
 };
 static_assert(DenseT32Smem::total <= 232448, "tf32 dense kernel shared memory exceeds 227 KB");
 
-__global__ void __launch_bounds__(kDenseT32Threads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDenseT32Threads, 1)
 vt_dense_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
                        const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUtensorMap map_bl,
                        const float* __restrict__ b3g, float* __restrict__ hbuf, long long n, int num_tiles) {
@@ -1124,12 +1126,17 @@ vt_dense_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_
   uint64_t* acc_empty = acc_full + 2;           // [2] the epilogue warps have folded it into their registers
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + DenseT32Smem::tmem_slot);
   const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  // the pair walks tiles 2 i and 2 i + 1 in lockstep (a trailing odd tile is all out-of-range rows: zero-filled
+  // loads, no stores)
+  const int tile_first = 2 * (int)cluster_id_x() + (int)rank, tile_step = 2 * (int)cluster_count_x();
+  const int pair_iters = (num_tiles + 1) / 2;       // iterations of pair p: tiles 2 p, 2 p + 1
 
   for (int i = tid; i < 256; i += kDenseT32Threads) reinterpret_cast<float*>(smem + DenseT32Smem::b3)[i] = b3g[i];
   if (tid == 0) {
     for (int s = 0; s < kTStages; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
+      mbar_init(&empty[s], 2);                   // this CTA's MMAs and the peer's (its multicast writes land here too)
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&acc_full[b], 1);
@@ -1144,12 +1151,13 @@ vt_dense_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_
   if (warp == 0) tmem_alloc<512>(tmem_slot);
   tc_fence_before_sync();
   __syncthreads();
+  cluster_sync_all();                            // the peer's barriers exist before anything is multicast at them
   tc_fence_after_sync();
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 0) {
     uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = tile_first, pit = (int)cluster_id_x(); pit < pair_iters; tile += tile_step, pit += (int)cluster_count_x()) {
       for (int kb = 0; kb < kTKBlocks; ++kb, ++it) {
         const uint32_t s = it % kTStages, ph = (it / kTStages) & 1;
         mbar_wait(&empty[s], ph ^ 1);
@@ -1158,8 +1166,9 @@ vt_dense_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_
           mbar_arrive_expect_tx(&full[s], kTStageBytes);
           tma_load_2d(st, &map_ah, kb * kTK, tile * kTM, &full[s]);
           tma_load_2d(st + kTABytes, &map_al, kb * kTK, tile * kTM, &full[s]);
-          tma_load_2d(st + 2 * kTABytes, &map_bh, kb * kTK, 0, &full[s]);
-          tma_load_2d(st + 2 * kTABytes + kTBBytes, &map_bl, kb * kTK, 0, &full[s]);
+          // my half of the W3 block (128 of its 256 rows), to both CTAs
+          tma_load_2d_multicast(st + 2 * kTABytes + rank * (kTBBytes / 2), &map_bh, kb * kTK, (int)rank * 128, &full[s], 3);
+          tma_load_2d_multicast(st + 2 * kTABytes + kTBBytes + rank * (kTBBytes / 2), &map_bl, kb * kTK, (int)rank * 128, &full[s], 3);
         }
         __syncwarp();
       }
@@ -1169,7 +1178,7 @@ vt_dense_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_
     const uint32_t base = smem_u32(smem);
     constexpr uint32_t hi = smem_desc_hi(1024, 2);
     uint32_t it = 0, run = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = tile_first, pit = (int)cluster_id_x(); pit < pair_iters; tile += tile_step, pit += (int)cluster_count_x()) {
       for (int r = 0; r < kTRuns; ++r, ++run) {
         const uint32_t buf = run & 1;
         mbar_wait(&acc_empty[buf], ((run >> 1) & 1) ^ 1);
@@ -1189,7 +1198,7 @@ vt_dense_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_
               mma_tf32_ss(tmem + buf * 256, desc64(ah + o, hi), desc64(bl + o, hi), idesc, 1);
               mma_tf32_ss(tmem + buf * 256, desc64(ah + o, hi), desc64(bh + o, hi), idesc, 1);
             }
-            mma_commit(&empty[s]);
+            mma_commit_multicast(&empty[s], 3);
             if (kk == kTRunBlocks - 1) mma_commit(&acc_full[buf]);
           }
           __syncwarp();
@@ -1200,7 +1209,7 @@ vt_dense_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_
     const int q = warp & 3, half = (warp - 2) >> 2;          // TMEM lane quarter, column half
     const float* b3s = reinterpret_cast<const float*>(smem + DenseT32Smem::b3) + half * 128;
     uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = tile_first, pit = (int)cluster_id_x(); pit < pair_iters; tile += tile_step, pit += (int)cluster_count_x()) {
       float acc[128];
 #pragma unroll
       for (int i = 0; i < 128; ++i) acc[i] = 0.f;
@@ -1245,6 +1254,7 @@ vt_dense_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_
   __syncwarp();
   tc_fence_before_sync();
   __syncthreads();
+  cluster_sync_all();                            // no multicast may target a CTA that has already exited
   if (warp == 0) tmem_dealloc<512>(tmem);
 }
 
@@ -1388,8 +1398,8 @@ int pack_vt_bf16(mdc_handle_s* h) {      // both tensor-core modes (MDC_MODE_BF1
       if (int e = h->vt_w3_bf16.reserve(2 * cnt * 4)) return e;
       MDC_CUDA(cudaMemcpy(h->vt_w3_bf16.ptr, img.data(), 2 * cnt * 4, cudaMemcpyHostToDevice));
       const float* base = reinterpret_cast<const float*>(h->vt_w3_bf16.ptr);
-      if (int e = make_kmajor_map(&maps[0], base, kVtH, true, 256)) return e;
-      if (int e = make_kmajor_map(&maps[1], base + cnt, kVtH, true, 256)) return e;
+      if (int e = make_kmajor_map(&maps[0], base, kVtH, true, 128)) return e;      // half a block per CTA of the pair
+      if (int e = make_kmajor_map(&maps[1], base + cnt, kVtH, true, 128)) return e;
     }
   }
   MDC_CUDA(cudaFuncSetAttribute(vt_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<false>::total));
@@ -1538,7 +1548,8 @@ int launch_vt_dense_head(mdc_handle_s* h, int64_t m, float* probs, float* dense,
     if (int e = make_kmajor_map(&map_ah, act, (uint64_t)m, true, kTM)) return e;
     if (int e = make_kmajor_map(&map_al, act + h->vt_act_elems, (uint64_t)m, true, kTM)) return e;
     const int tiles = (int)((m + kTM - 1) / kTM);
-    const unsigned grid_d = (unsigned)(tiles < h->num_sms ? tiles : h->num_sms);
+    const int pairs = (tiles + 1) / 2, pairs_max = h->num_sms / 2;
+    const unsigned grid_d = 2u * (unsigned)(pairs < pairs_max ? pairs : pairs_max);
     vt_dense_tf32x3_kernel<<<grid_d, kDenseT32Threads, DenseT32Smem::total, stream>>>(map_ah, map_al, wmaps[0], wmaps[1],
                                                                                        b3, hb, m, tiles);
   }
