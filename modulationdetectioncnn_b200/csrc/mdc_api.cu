@@ -56,10 +56,6 @@ struct HostPipe {
   cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr;
   cudaEvent_t e_h2d[kSlots] = {}, e_comp[kSlots] = {}, e_d2h[kSlots] = {};
   cudaEvent_t e_pass[2] = {}, e_pass_d2h[2] = {};      // tensor-core VT path: per-pass output buffers
-  // streaming bf16 path: whole-pass frame buffers, "frames landed" counters the conv kernel polls
-  DeviceBuffer xp[2], flags;
-  cudaEvent_t e_conv[2] = {};
-  unsigned landed[2] = {0, 0};                         // host mirror of the (monotonic, wrapping) counters
   DeviceBuffer x[kSlots], o0[kSlots], o1[kSlots], o2[kSlots];
   DeviceBuffer hist;
   int init() {
@@ -75,10 +71,7 @@ struct HostPipe {
     for (int i = 0; i < 2; ++i) {
       MDC_CUDA(cudaEventCreateWithFlags(&e_pass[i], cudaEventDisableTiming));
       MDC_CUDA(cudaEventCreateWithFlags(&e_pass_d2h[i], cudaEventDisableTiming));
-      MDC_CUDA(cudaEventCreateWithFlags(&e_conv[i], cudaEventDisableTiming));
     }
-    if (int e = flags.reserve(256)) return e;
-    MDC_CUDA(cudaMemset(flags.ptr, 0, 256));
     return hist.reserve(kMaxClasses * kMaxClasses * sizeof(unsigned long long));
   }
   void destroy() {
@@ -88,11 +81,7 @@ struct HostPipe {
       cudaEventDestroy(e_h2d[i]); cudaEventDestroy(e_comp[i]); cudaEventDestroy(e_d2h[i]);
       x[i].release(); o0[i].release(); o1[i].release(); o2[i].release();
     }
-    for (int i = 0; i < 2; ++i) {
-      cudaEventDestroy(e_pass[i]); cudaEventDestroy(e_pass_d2h[i]); cudaEventDestroy(e_conv[i]);
-      xp[i].release();
-    }
-    flags.release();
+    for (int i = 0; i < 2; ++i) { cudaEventDestroy(e_pass[i]); cudaEventDestroy(e_pass_d2h[i]); }
     hist.release();
     cudaStreamDestroy(s_h2d); cudaStreamDestroy(s_comp); cudaStreamDestroy(s_d2h);
     s_h2d = nullptr;
@@ -238,20 +227,6 @@ static int run_vt_host_pipeline(mdc_handle_s* h, const float* x, int64_t n, floa
     if (dense) if (int e = P.o1[b].reserve((size_t)cap * C * sizeof(float))) return e;
     if (cls) if (int e = P.o2[b].reserve((size_t)cap * sizeof(int32_t))) return e;
   }
-  // MDC_VT_TIMELINE=1 (diagnostic): timing events after every copy / kernel, printed relative to the first
-  static const bool timeline = getenv("MDC_VT_TIMELINE") != nullptr;
-  std::vector<std::pair<const char*, cudaEvent_t>> tl;
-  auto mark = [&](const char* what, cudaStream_t st) {
-    if (!timeline) return;
-    cudaEvent_t e;
-    cudaEventCreate(&e);
-    cudaEventRecord(e, st);
-    tl.emplace_back(what, e);
-  };
-  if (timeline) {
-    cudaStreamSynchronize(P.s_comp);
-    mark("start", P.s_h2d);
-  }
   int64_t i = 0, pi = 0;
   for (int64_t p0 = 0; p0 < n; p0 += pass, ++pi) {
     const int64_t pm = (n - p0) < pass ? (n - p0) : pass;
@@ -265,111 +240,9 @@ static int run_vt_host_pipeline(mdc_handle_s* h, const float* x, int64_t n, floa
       MDC_CUDA(cudaMemcpyAsync(P.x[k].ptr, x + (p0 + c0) * kFrameElems, (size_t)m * kFrameElems * sizeof(float),
                                cudaMemcpyHostToDevice, P.s_h2d));
       MDC_CUDA(cudaEventRecord(P.e_h2d[k], P.s_h2d));
-      mark("h2d", P.s_h2d);
       MDC_CUDA(cudaStreamWaitEvent(P.s_comp, P.e_h2d[k], 0));
-      if (int e = launch_vt_conv(h, (const float*)P.x[k].ptr, m, c0, P.s_comp, nullptr, 0)) return e;
+      if (int e = launch_vt_conv(h, (const float*)P.x[k].ptr, m, c0, P.s_comp)) return e;
       MDC_CUDA(cudaEventRecord(P.e_comp[k], P.s_comp));
-      mark("conv", P.s_comp);
-    }
-    if (pi >= 2) MDC_CUDA(cudaStreamWaitEvent(P.s_comp, P.e_pass_d2h[ob], 0));
-    if (int e = launch_vt_dense_head(h, pm, probs ? (float*)P.o0[ob].ptr : nullptr, dense ? (float*)P.o1[ob].ptr : nullptr,
-                                     cls ? (int32_t*)P.o2[ob].ptr : nullptr,
-                                     hist ? (unsigned long long*)P.hist.ptr : nullptr, P.s_comp))
-      return e;
-    MDC_CUDA(cudaEventRecord(P.e_pass[ob], P.s_comp));
-    mark("dense", P.s_comp);
-    MDC_CUDA(cudaStreamWaitEvent(P.s_d2h, P.e_pass[ob], 0));
-    if (probs) MDC_CUDA(cudaMemcpyAsync(probs + p0 * C, P.o0[ob].ptr, (size_t)pm * C * sizeof(float), cudaMemcpyDeviceToHost, P.s_d2h));
-    if (dense) MDC_CUDA(cudaMemcpyAsync(dense + p0 * C, P.o1[ob].ptr, (size_t)pm * C * sizeof(float), cudaMemcpyDeviceToHost, P.s_d2h));
-    if (cls) MDC_CUDA(cudaMemcpyAsync(cls + p0, P.o2[ob].ptr, (size_t)pm * sizeof(int32_t), cudaMemcpyDeviceToHost, P.s_d2h));
-    MDC_CUDA(cudaEventRecord(P.e_pass_d2h[ob], P.s_d2h));
-    mark("d2h", P.s_d2h);
-  }
-  if (timeline) {
-    cudaStreamSynchronize(P.s_d2h);
-    cudaStreamSynchronize(P.s_comp);
-    for (auto& ev : tl) {
-      float ms = 0.f;
-      cudaEventElapsedTime(&ms, tl[0].second, ev.second);
-      fprintf(stderr, "  %-6s %8.3f ms\n", ev.first, ms);
-    }
-    for (auto& ev : tl) cudaEventDestroy(ev.second);
-  }
-  if (hist) {
-    MDC_CUDA(cudaStreamSynchronize(P.s_comp));
-    MDC_CUDA(cudaMemcpyAsync(hist, P.hist.ptr, C * sizeof(unsigned long long), cudaMemcpyDeviceToHost, P.s_d2h));
-  }
-  MDC_CUDA(cudaStreamSynchronize(P.s_d2h));
-  MDC_CUDA(cudaStreamSynchronize(P.s_comp));
-  return MDC_OK;
-}
-
-// cuStreamWriteValue32: a 4-byte device write in stream order (after the copies enqueued before it)
-typedef int (*StreamWrite32Fn)(cudaStream_t, unsigned long long, unsigned, unsigned);
-static StreamWrite32Fn get_stream_write32() {
-  static StreamWrite32Fn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<StreamWrite32Fn>(p);
-  }
-  return fn;
-}
-
-// bf16 VT-CNN2 from host buffers, streaming form: ONE persistent conv launch per pass that starts at once and
-// consumes the frames while the copy engine is still delivering them - after every 8 MiB chunk the copy stream
-// bumps a device counter (cuStreamWriteValue32) and the kernel's TMA warp polls it before it fetches a
-// super-tile's frames.  Against one launch per chunk this removes ~30 us of launch / prologue / drain per
-// chunk (measured with MDC_VT_TIMELINE), which was the whole gap between the host-buffer and the
-// device-resident rate.
-static int run_vt_host_streaming(mdc_handle_s* h, const float* x, int64_t n, float* probs, float* dense, int32_t* cls,
-                                 unsigned long long* hist, StreamWrite32Fn write32) {
-  if (!h->pipe) h->pipe = new HostPipe();
-  HostPipe& P = *h->pipe;
-  if (int e = P.init()) return e;
-  const int C = h->C;
-  static const int64_t pass = getenv("MDC_VT_PASS") ? atoll(getenv("MDC_VT_PASS")) : 32768;
-  static const int64_t chunk = getenv("MDC_VT_CHUNK") ? atoll(getenv("MDC_VT_CHUNK")) : 8192;
-  static const int64_t first = getenv("MDC_VT_FIRST") ? atoll(getenv("MDC_VT_FIRST")) : 2048;
-  const int64_t cap = n < pass ? n : pass;
-  if (int e = vt_reserve(h, cap)) return e;
-  if (hist) MDC_CUDA(cudaMemsetAsync(P.hist.ptr, 0, C * sizeof(unsigned long long), P.s_comp));
-  for (int b = 0; b < 2; ++b) {
-    if (b == 0 || n > pass) if (int e = P.xp[b].reserve((size_t)cap * kFrameElems * sizeof(float))) return e;
-    if (probs) if (int e = P.o0[b].reserve((size_t)cap * C * sizeof(float))) return e;
-    if (dense) if (int e = P.o1[b].reserve((size_t)cap * C * sizeof(float))) return e;
-    if (cls) if (int e = P.o2[b].reserve((size_t)cap * sizeof(int32_t))) return e;
-  }
-  unsigned* flags = reinterpret_cast<unsigned*>(P.flags.ptr);      // words 0 / 16: counters, 8 / 24: kernel time-outs
-  int64_t pi = 0;
-  for (int64_t p0 = 0; p0 < n; p0 += pass, ++pi) {
-    const int64_t pm = (n - p0) < pass ? (n - p0) : pass;
-    const int ob = (int)(pi & 1);
-    float* xdev = reinterpret_cast<float*>(P.xp[ob].ptr);
-    // the pass's frame buffer is free once the conv launch of two passes ago has finished
-    if (pi >= 2) MDC_CUDA(cudaStreamWaitEvent(P.s_h2d, P.e_conv[ob], 0));
-    if (int e = launch_vt_conv(h, xdev, pm, 0, P.s_comp, flags + 16 * ob, P.landed[ob])) return e;
-    MDC_CUDA(cudaEventRecord(P.e_conv[ob], P.s_comp));
-    for (int64_t c0 = 0, step = 0; c0 < pm; c0 += step) {
-      step = (p0 == 0 && c0 == 0 && pm > 2 * first) ? first : chunk;      // nothing overlaps the very first copy
-      const int64_t m = (pm - c0) < step ? (pm - c0) : step;
-      MDC_CUDA(cudaMemcpyAsync(xdev + c0 * kFrameElems, x + (p0 + c0) * kFrameElems, (size_t)m * kFrameElems * sizeof(float),
-                               cudaMemcpyHostToDevice, P.s_h2d));
-      P.landed[ob] += (unsigned)m;
-      const int rc = write32(P.s_h2d, (unsigned long long)(uintptr_t)(flags + 16 * ob), P.landed[ob], 0);
-      if (rc != 0) {
-        // never leave the launched kernel polling: release it (its results are discarded with the error)
-        P.landed[ob] += (unsigned)(pm - c0 - m);
-        cudaMemcpyAsync(flags + 16 * ob, &P.landed[ob], sizeof(unsigned), cudaMemcpyHostToDevice, P.s_h2d);
-        cudaStreamSynchronize(P.s_h2d);
-        cudaStreamSynchronize(P.s_comp);
-        set_error("cuStreamWriteValue32 failed with CUresult %d", rc);
-        return MDC_ERR_CUDA;
-      }
     }
     if (pi >= 2) MDC_CUDA(cudaStreamWaitEvent(P.s_comp, P.e_pass_d2h[ob], 0));
     if (int e = launch_vt_dense_head(h, pm, probs ? (float*)P.o0[ob].ptr : nullptr, dense ? (float*)P.o1[ob].ptr : nullptr,
@@ -389,15 +262,6 @@ static int run_vt_host_streaming(mdc_handle_s* h, const float* x, int64_t n, flo
   }
   MDC_CUDA(cudaStreamSynchronize(P.s_d2h));
   MDC_CUDA(cudaStreamSynchronize(P.s_comp));
-  MDC_CUDA(cudaStreamSynchronize(P.s_h2d));
-  unsigned timed_out[32] = {};
-  MDC_CUDA(cudaMemcpy(timed_out, flags, sizeof(timed_out), cudaMemcpyDeviceToHost));
-  if (timed_out[8] | timed_out[24]) {
-    MDC_CUDA(cudaMemset(flags + 8, 0, 4));
-    MDC_CUDA(cudaMemset(flags + 24, 0, 4));
-    set_error("streaming conv kernel timed out waiting for host frames");
-    return MDC_ERR_CUDA;
-  }
   return MDC_OK;
 }
 
@@ -602,14 +466,8 @@ int mdc_predict_f32_host(mdc_handle_t h, const float* x_host, int64_t n, float* 
     if (hist_host) memset(hist_host, 0, h->C * sizeof(unsigned long long));
     return MDC_OK;
   }
-  if (h->model == MDC_MODEL_VT && h->mode != MDC_MODE_FP32) {
-    // MDC_VT_STREAMING=0 (tuning aid) falls back to one conv launch per copied chunk
-    static const bool streaming = !(getenv("MDC_VT_STREAMING") && atoi(getenv("MDC_VT_STREAMING")) == 0);
-    StreamWrite32Fn w32 = get_stream_write32();
-    if (h->mode == MDC_MODE_BF16 && streaming && w32 != nullptr)
-      return run_vt_host_streaming(h, x_host, n, probs_host, dense_host, cls_host, hist_host, w32);
+  if (h->model == MDC_MODEL_VT && h->mode != MDC_MODE_FP32)
     return run_vt_host_pipeline(h, x_host, n, probs_host, dense_host, cls_host, hist_host);
-  }
   const int64_t chunk = 16384;
   return run_host_pipeline<float, float, float>(
       h, x_host, n, probs_host, dense_host, cls_host, hist_host, chunk,

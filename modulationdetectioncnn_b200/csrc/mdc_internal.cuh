@@ -114,9 +114,7 @@ int launch_vt_bf16(mdc_handle_s* h, const float* x, int64_t n, float* probs, flo
 // dense1 + head once per pass)
 int64_t vt_pass_frames(const mdc_handle_s* h);
 int vt_reserve(mdc_handle_s* h, int64_t frames);
-// ready != NULL: streaming launch - frame f of this launch may be read once *ready - ready_base > f (wrap-safe)
-int launch_vt_conv(mdc_handle_s* h, const float* x, int64_t m, int64_t frame_offset, cudaStream_t stream,
-                   const unsigned* ready, unsigned ready_base);
+int launch_vt_conv(mdc_handle_s* h, const float* x, int64_t m, int64_t frame_offset, cudaStream_t stream);
 int launch_vt_dense_head(mdc_handle_s* h, int64_t m, float* probs, float* dense, int32_t* cls,
                          unsigned long long* hist, cudaStream_t stream);
 int pack_tiny(mdc_handle_s* h);

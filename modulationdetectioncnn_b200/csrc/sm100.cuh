@@ -113,14 +113,6 @@ __device__ __forceinline__ void cluster_sync_all() {
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
-// generic-proxy accesses (any state space) ordered before later async-proxy (TMA) accesses
-__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
-// system-scope acquire load: sees values written by the host / copy engines in stream order
-__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
 __device__ __forceinline__ void fence_acq_rel_cluster() { asm volatile("fence.acq_rel.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before_sync() {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

@@ -156,8 +156,7 @@ template <bool TF32>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ConvCfg<TF32>::kThreads, 1)
 vt_conv_kernel(const __grid_constant__ ConvW1 w1c, const float* __restrict__ x, long long n,
                const float* __restrict__ b2g, const uint8_t* __restrict__ w2img,
-               void* __restrict__ act0, void* __restrict__ act1, long long num_st, int dbg_rt,
-               const unsigned* __restrict__ ready, unsigned ready_base) {
+               void* __restrict__ act0, void* __restrict__ act1, long long num_st, int dbg_rt) {
   using ConvSmem = ConvCfg<TF32>;
   constexpr int kStages = ConvSmem::kStages, kChunks = ConvSmem::kChunks;
   constexpr int kASlot = ConvSmem::kASlot, kBSlot = ConvSmem::kBSlot, kAImg = ConvSmem::kAImg, kBImg = ConvSmem::kBImg;
@@ -224,23 +223,6 @@ vt_conv_kernel(const __grid_constant__ ConvW1 w1c, const float* __restrict__ x, 
       const uint32_t nf = left <= 0 ? 0u : (left < kXFrames ? (uint32_t)left : (uint32_t)kXFrames);
       const uint32_t b = j & 1;
       mbar_wait(&x_empty[b], ((j >> 1) & 1) ^ 1);
-      if (ready != nullptr && nf) {
-        // streaming launch: the host copy engine is still filling x; a counter written in stream order after
-        // every chunk (cuStreamWriteValue32) says how many frames of this launch have landed
-        if (elect_one()) {
-          const unsigned need = ready_base + (unsigned)(f0 + nf);
-          unsigned polls = 0;
-          while ((int)(ld_acquire_sys_u32(ready) - need) < 0) {
-            __nanosleep(256);
-            if (++polls > (1u << 24)) {          // seconds without data: report (word 8) instead of hanging the GPU
-              atomicExch(const_cast<unsigned*>(ready) + 8, 1u);
-              break;
-            }
-          }
-          fence_proxy_async_all();
-        }
-        __syncwarp();
-      }
       if (elect_one()) {
         mbar_arrive_expect_tx(&x_full[b], nf * 1024);
         if (nf) bulk_g2s(smem + ConvSmem::xs + b * (kXFrames * 1024), x + f0 * 256, nf * 1024, &x_full[b]);
@@ -1427,8 +1409,7 @@ int vt_reserve(mdc_handle_s* h, int64_t frames) {
 }
 
 // conv1 + conv2 of m frames at x -> activations of frames [frame_offset, frame_offset + m) of the pass
-int launch_vt_conv(mdc_handle_s* h, const float* x, int64_t m, int64_t frame_offset, cudaStream_t stream,
-                   const unsigned* ready, unsigned ready_base) {
+int launch_vt_conv(mdc_handle_s* h, const float* x, int64_t m, int64_t frame_offset, cudaStream_t stream) {
   const bool tf32 = h->mode == MDC_MODE_TF32X3;
   if (m == 0) return MDC_OK;
   const size_t off = (size_t)frame_offset * kVtFlat;
@@ -1442,7 +1423,7 @@ int launch_vt_conv(mdc_handle_s* h, const float* x, int64_t m, int64_t frame_off
   // MDC_VT_CONV=n240 selects the experimental second bf16 formulation (taps as N) for A/B timing: it is
   // numerically identical but slower (2.25 ms against 1.35 ms per 65,536 frames), see DESIGN.md section 5.1
   static const bool use_n240 = getenv("MDC_VT_CONV") && !strcmp(getenv("MDC_VT_CONV"), "n240");
-  if (!tf32 && use_n240 && ready == nullptr) {
+  if (!tf32 && use_n240) {
     const long long num_tiles = (m * 132 + Conv240::kOutRows - 1) / Conv240::kOutRows;
     const long long pairs_needed = (num_tiles + 1) / 2, pairs_max = h->num_sms / 2;
     const unsigned grid_c = 2u * (unsigned)(pairs_needed < pairs_max ? pairs_needed : pairs_max);
@@ -1481,9 +1462,9 @@ int launch_vt_conv(mdc_handle_s* h, const float* x, int64_t m, int64_t frame_off
   const uint8_t* w2 = reinterpret_cast<const uint8_t*>(h->vt_w2_bf16.ptr);
   prof_begin(h, stream);
   if (tf32)
-    vt_conv_kernel<true><<<grid_c, ConvCfg<true>::kThreads, ConvCfg<true>::total, stream>>>(w1c, x, m, b2, w2, act0, act1, num_st, dbg, ready, ready_base);
+    vt_conv_kernel<true><<<grid_c, ConvCfg<true>::kThreads, ConvCfg<true>::total, stream>>>(w1c, x, m, b2, w2, act0, act1, num_st, dbg);
   else
-    vt_conv_kernel<false><<<grid_c, ConvCfg<false>::kThreads, ConvCfg<false>::total, stream>>>(w1c, x, m, b2, w2, act0, act1, num_st, dbg, ready, ready_base);
+    vt_conv_kernel<false><<<grid_c, ConvCfg<false>::kThreads, ConvCfg<false>::total, stream>>>(w1c, x, m, b2, w2, act0, act1, num_st, dbg);
   prof_end(h, stream);
   h->launches += 1;
   MDC_CUDA(cudaGetLastError());
@@ -1565,7 +1546,7 @@ int launch_vt_bf16(mdc_handle_s* h, const float* x, int64_t n, float* probs, flo
   if (int e = vt_reserve(h, n < CH ? n : CH)) return e;
   for (int64_t s = 0; s < n; s += CH) {
     const int64_t m = (n - s) < CH ? (n - s) : CH;
-    if (int e = launch_vt_conv(h, x + s * 256, m, 0, stream, nullptr, 0)) return e;
+    if (int e = launch_vt_conv(h, x + s * 256, m, 0, stream)) return e;
     if (int e = launch_vt_dense_head(h, m, probs ? probs + s * h->C : nullptr, dense ? dense + s * h->C : nullptr,
                                      cls ? cls + s : nullptr, hist, stream))
       return e;
