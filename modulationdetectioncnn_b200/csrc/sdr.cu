@@ -11,69 +11,58 @@
 //   frames_q612  i32 [n/128][256]      0-127 I, 128-255 Q     -> mdc_predict_q612 (test_table map, sv:88-89,102)
 //   fwht_blocks  i32 [n/1024][2][1024] Q6.12 I block, Q block -> mdc_fwht_i32 (2 spectra per block)
 //
-// HBM-bound: 2 B/sample in, 8 B/sample per requested output.  One thread per 8 samples: a 16-B
-// load, then 32-B contiguous runs per row - half a warp writes one whole 512-B frame row.
+// HBM-bound: 2 B/sample in, 8 B/sample per requested output.
 #include "mdc_internal.cuh"
 
 namespace mdc {
 
-__device__ __forceinline__ uint4 ldg_stream_u4(const uint4* p) {
-  uint4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+__device__ __forceinline__ uint2 ldg_stream_u2(const uint2* p) {
+  uint2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
   return r;
 }
 
+// One thread per 4 samples (an 8-B load); a warp covers exactly one 128-sample frame, so every store
+// instruction writes one full 512-B row (16 B per lane, contiguous across the warp: whole sectors - with 8
+// samples per thread the 32-B runs left every store half-filling its sectors and the L1 write path at 86 %).
 __global__ void __launch_bounds__(256)
-sdr_ingest_kernel(const uint4* __restrict__ iq, long long n_groups, float* __restrict__ f32,
+sdr_ingest_kernel(const uint2* __restrict__ iq, long long n_groups, float* __restrict__ f32,
                   int* __restrict__ q612, int* __restrict__ fwht) {
   for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < n_groups;
        g += (long long)gridDim.x * blockDim.x) {
-    const uint4 raw = ldg_stream_u4(iq + g);                 // samples 8 g .. 8 g + 7
-    const unsigned w[4] = {raw.x, raw.y, raw.z, raw.w};
-    int qi[8], qq[8];
+    const uint2 raw = ldg_stream_u2(iq + g);                 // samples 4 g .. 4 g + 3
+    const unsigned w[2] = {raw.x, raw.y};
+    int qi[4], qq[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < 2; ++k) {
       qi[2 * k] = (2 * (int)(w[k] & 0xFF) - 255) * 16;
       qq[2 * k] = (2 * (int)((w[k] >> 8) & 0xFF) - 255) * 16;
       qi[2 * k + 1] = (2 * (int)((w[k] >> 16) & 0xFF) - 255) * 16;
       qq[2 * k + 1] = (2 * (int)(w[k] >> 24) - 255) * 16;
     }
-    const long long frame = g >> 4;                          // 16 groups per 128-sample frame
-    const int off = (int)(g & 15) * 8;
+    const long long frame = g >> 5;                          // 32 groups per 128-sample frame
+    const int off = (int)(g & 31) * 4;
     if (f32) {
-      float4* di = reinterpret_cast<float4*>(f32 + frame * 256 + off);
-      float4* dq = reinterpret_cast<float4*>(f32 + frame * 256 + 128 + off);
       constexpr float s = 1.0f / 4096.0f;                    // exact: |q| < 2^13
-      __stcs(di + 0, make_float4(qi[0] * s, qi[1] * s, qi[2] * s, qi[3] * s));
-      __stcs(di + 1, make_float4(qi[4] * s, qi[5] * s, qi[6] * s, qi[7] * s));
-      __stcs(dq + 0, make_float4(qq[0] * s, qq[1] * s, qq[2] * s, qq[3] * s));
-      __stcs(dq + 1, make_float4(qq[4] * s, qq[5] * s, qq[6] * s, qq[7] * s));
+      __stcs(reinterpret_cast<float4*>(f32 + frame * 256 + off), make_float4(qi[0] * s, qi[1] * s, qi[2] * s, qi[3] * s));
+      __stcs(reinterpret_cast<float4*>(f32 + frame * 256 + 128 + off), make_float4(qq[0] * s, qq[1] * s, qq[2] * s, qq[3] * s));
     }
     if (q612) {
-      int4* di = reinterpret_cast<int4*>(q612 + frame * 256 + off);
-      int4* dq = reinterpret_cast<int4*>(q612 + frame * 256 + 128 + off);
-      __stcs(di + 0, make_int4(qi[0], qi[1], qi[2], qi[3]));
-      __stcs(di + 1, make_int4(qi[4], qi[5], qi[6], qi[7]));
-      __stcs(dq + 0, make_int4(qq[0], qq[1], qq[2], qq[3]));
-      __stcs(dq + 1, make_int4(qq[4], qq[5], qq[6], qq[7]));
+      __stcs(reinterpret_cast<int4*>(q612 + frame * 256 + off), make_int4(qi[0], qi[1], qi[2], qi[3]));
+      __stcs(reinterpret_cast<int4*>(q612 + frame * 256 + 128 + off), make_int4(qq[0], qq[1], qq[2], qq[3]));
     }
     if (fwht) {
-      const long long block = g >> 7;                        // 128 groups per 1024-sample block
-      const int boff = (int)(g & 127) * 8;
-      int4* di = reinterpret_cast<int4*>(fwht + block * 2048 + boff);
-      int4* dq = reinterpret_cast<int4*>(fwht + block * 2048 + 1024 + boff);
-      __stcs(di + 0, make_int4(qi[0], qi[1], qi[2], qi[3]));
-      __stcs(di + 1, make_int4(qi[4], qi[5], qi[6], qi[7]));
-      __stcs(dq + 0, make_int4(qq[0], qq[1], qq[2], qq[3]));
-      __stcs(dq + 1, make_int4(qq[4], qq[5], qq[6], qq[7]));
+      const long long block = g >> 8;                        // 256 groups per 1024-sample block
+      const int boff = (int)(g & 255) * 4;
+      __stcs(reinterpret_cast<int4*>(fwht + block * 2048 + boff), make_int4(qi[0], qi[1], qi[2], qi[3]));
+      __stcs(reinterpret_cast<int4*>(fwht + block * 2048 + 1024 + boff), make_int4(qq[0], qq[1], qq[2], qq[3]));
     }
   }
 }
 
 int launch_sdr_ingest(const uint8_t* iq, int64_t n_samples, float* f32, int32_t* q612, int32_t* fwht,
                       cudaStream_t stream) {
-  const long long groups = n_samples / 8;
+  const long long groups = n_samples / 4;
   if (groups == 0) return MDC_OK;
   int dev = 0, sms = 148;
   MDC_CUDA(cudaGetDevice(&dev));
@@ -82,7 +71,7 @@ int launch_sdr_ingest(const uint8_t* iq, int64_t n_samples, float* f32, int32_t*
   long long blocks = (groups + 255) / 256;
   const long long maxb = (long long)sms * bpsm;
   if (blocks > maxb) blocks = maxb;
-  sdr_ingest_kernel<<<(unsigned)blocks, 256, 0, stream>>>(reinterpret_cast<const uint4*>(iq), groups, f32, q612, fwht);
+  sdr_ingest_kernel<<<(unsigned)blocks, 256, 0, stream>>>(reinterpret_cast<const uint2*>(iq), groups, f32, q612, fwht);
   MDC_CUDA(cudaGetLastError());
   return MDC_OK;
 }
