@@ -196,6 +196,62 @@ tiny_f32_kernel(const TinyParams p, const float4* __restrict__ dmain, const floa
         }
       }
     }
+    if constexpr (R == 2 && C <= 4) {
+      // Cross-lane sums of the 2 x C partials by recursive halving: every step halves the values a lane carries
+      // instead of reducing each of them over all 32 lanes (9 shuffles instead of 10 C), and leaves the sum for
+      // (frame r, class c) in the lanes with bit 4 = r, bits 3..2 = c.  One softmax per warp serves both frames.
+      float v[8];
+#pragma unroll
+      for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (c < C) {
+            float lo, hi;
+            f2_unpack(acc[r][c], lo, hi);
+            v[r * 4 + c] = (lo + hi) + tail[r][c];
+          } else {
+            v[r * 4 + c] = 0.f;
+          }
+        }
+      const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+      float w4[4], w2[2];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) w4[j] = (b4 ? v[4 + j] : v[j]) + __shfl_xor_sync(0xffffffffu, b4 ? v[j] : v[4 + j], 16);
+#pragma unroll
+      for (int j = 0; j < 2; ++j) w2[j] = (b3 ? w4[2 + j] : w4[j]) + __shfl_xor_sync(0xffffffffu, b3 ? w4[j] : w4[2 + j], 8);
+      float t = (b2 ? w2[1] : w2[0]) + __shfl_xor_sync(0xffffffffu, b2 ? w2[0] : w2[1], 4);
+      t += __shfl_xor_sync(0xffffffffu, t, 2);
+      t += __shfl_xor_sync(0xffffffffu, t, 1);
+      const int myc = (lane >> 2) & 3, half = lane & 16;
+      float bsel = p.bias[0];
+#pragma unroll
+      for (int c = 1; c < C; ++c) if (myc == c) bsel = p.bias[c];
+      t = fmaxf(t + bsel, 0.f);
+      float z[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) z[c] = __shfl_sync(0xffffffffu, t, half + 4 * c);
+      const long long f = f0 + (lane >> 4);
+      if (f < n) {
+        int best = 0;
+        float m = z[0];
+#pragma unroll
+        for (int c = 1; c < C; ++c) if (z[c] > m) { m = z[c]; best = c; }
+        float e[C], sum = 0.f;
+#pragma unroll
+        for (int c = 0; c < C; ++c) { e[c] = expf(z[c] - m); sum += e[c]; }
+        const float inv = 1.0f / sum;
+        const int l16 = lane & 15;                 // lane c of each half-warp writes class c of its frame
+        float zsel = z[0], psel = e[0] * inv;
+#pragma unroll
+        for (int c = 1; c < C; ++c) if (l16 == c) { zsel = z[c]; psel = e[c] * inv; }
+        if (l16 < C) {
+          if (dense) dense[f * C + l16] = zsel;
+          if (probs) probs[f * C + l16] = psel;
+        }
+        if (l16 == 0 && cls) cls[f] = best;
+        cnt += (l16 == best);
+      }
+    } else {
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       float z[C];
@@ -230,8 +286,17 @@ tiny_f32_kernel(const TinyParams p, const float4* __restrict__ dmain, const floa
         cnt += (lane == best);
       }
     }
+    }
   }
-  if (hist && lane < C && cnt) atomicAdd(hist + lane, (unsigned long long)cnt);
+  if (hist) {
+    if constexpr (R == 2 && C <= 4) {
+      // lanes c and 16 + c counted class c for the even and the odd frames of this warp
+      cnt += __shfl_xor_sync(0xffffffffu, cnt, 16);
+      if (lane < C && cnt) atomicAdd(hist + lane, (unsigned long long)cnt);
+    } else {
+      if (lane < C && cnt) atomicAdd(hist + lane, (unsigned long long)cnt);
+    }
+  }
 }
 
 __device__ __forceinline__ float4 ldg_stream_f4(const float4* p) {
