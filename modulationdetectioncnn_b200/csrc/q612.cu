@@ -259,6 +259,9 @@ int launch_q612(mdc_handle_s* h, const int32_t* x, int64_t n, int32_t* out, int3
   if (h->F == 3 && h->C == 3) {
     if (variant) q612_kernel<3, 3, false, 4><<<(unsigned)blocks, threads, 0, stream>>>(p, d4, x4, n, out, pre, cls, hist);
     else q612_kernel<3, 3, true, 2><<<(unsigned)blocks, threads, 0, stream>>>(p, d4, x4, n, out, pre, cls, hist);
+  } else if (h->F == 10 && h->C == 3) {
+    // the 10-filter model (DenseWeights1.txt): 60 ROM rows per lane do not fit registers, they come through L1
+    q612_kernel<10, 3, false, 2><<<(unsigned)blocks, threads, 0, stream>>>(p, d4, x4, n, out, pre, cls, hist);
   } else {
     q612_generic_kernel<<<(unsigned)blocks, threads, 0, stream>>>(p, d4, x4, n, out, pre, cls, hist);
   }

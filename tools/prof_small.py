@@ -44,6 +44,14 @@ if which in ("all", "q612"):
     q.set_tables(QWeights(g["A_conv_tab"], g["A_dense_bias"], g["A_dense_tabs"]))
     timeit("q612", lambda: _lib.check(lib.mdc_predict_q612(q._h.ptr, x.data_ptr(), n, o.data_ptr(), None, None, None, stream)), 1036, n)
     del x, o
+if which in ("all", "q612f10"):
+    from modulationdetectioncnn_b200 import export
+    x = torch.randn((n, 256), device=dev).mul_(32).trunc_().to(torch.int32)
+    o = torch.empty((n, 3), dtype=torch.int32, device=dev)
+    q10 = FixedPointCNN2(10, 3)
+    q10.set_tables(export.qweights_from_dense_dump([hw[f"E_f10_{k}"] for k in ("conv_k", "conv_b", "dense_k", "dense_b")], g["E_dense_flat"]))
+    timeit("q612f10", lambda: _lib.check(lib.mdc_predict_q612(q10._h.ptr, x.data_ptr(), n, o.data_ptr(), None, None, None, stream)), 1036, n)
+    del x, o
 for tag, key in (("tiny3", "A_3conv"), ("tiny10", "E_f10")):
     if which in ("all", tag):
         w = [hw[f"{key}_{k}"] for k in ("conv_k", "conv_b", "dense_k", "dense_b")]
