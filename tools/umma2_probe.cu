@@ -17,16 +17,13 @@ constexpr int RA = 136;     // A rows staged per CTA (128 + halo)
 constexpr int REP = 4096;
 
 __device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128)
 probe2(const __nv_bfloat16* __restrict__ Ag, const __nv_bfloat16* __restrict__ Bg, float* __restrict__ D, int N, int shift,
-       int rate, long long* cyc) {
+       int rate, long long* cyc, int commit_every) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar;
+  __shared__ __align__(8) uint64_t bar2;       // absorbs the extra commits of the commit-cost experiment
   __shared__ uint32_t tmem_base;
   const int tid = threadIdx.x, warp = uniform_warp_idx();
   const uint32_t rank = cluster_rank();
@@ -42,7 +39,7 @@ probe2(const __nv_bfloat16* __restrict__ Ag, const __nv_bfloat16* __restrict__ B
     int row = i / K, k = i % K;
     *reinterpret_cast<__nv_bfloat16*>(sB + ((k / 8) * NH + row) * 16 + (k % 8) * 2) = Bg[(NH * rank + row) * K + k];
   }
-  if (tid == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+  if (tid == 0) { mbar_init(&bar, 1); mbar_init(&bar2, 1 << 19); fence_barrier_init(); }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base)), "n"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
@@ -62,7 +59,15 @@ probe2(const __nv_bfloat16* __restrict__ Ag, const __nv_bfloat16* __restrict__ B
       const uint32_t b_lo = smem_desc_lo(smem_u32(sB), NH * 16);
       t0 = clock64();
       const int reps = rate ? REP / 4 : 1;
+      int since = 0;
       for (int r = 0; r < reps; ++r) {
+        if (commit_every > 0 && (since += K / 16) >= commit_every) {
+          since = 0;
+          asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                           smem_u32(&bar2)),
+                       "h"((uint16_t)3)
+                       : "memory");
+        }
 #pragma unroll
         for (int s = 0; s < K / 16; ++s) {
           const uint64_t ad = desc64(a_lo + ((2 * s * RA * 16) >> 4), hi), bd = desc64(b_lo + ((2 * s * NH * 16) >> 4), hi);
@@ -103,6 +108,7 @@ int main(int argc, char** argv) {
   const int N = atoi(argv[2]);
   const int shift = (!rate && argc > 3) ? atoi(argv[3]) : 0;
   const int grid = (rate && argc > 3) ? atoi(argv[3]) : 2;
+  const int commit_every = (rate && argc > 4) ? atoi(argv[4]) : 0;   // extra tcgen05.commit after every this many MMAs
   const int RT = 128 + RA;   // A rows in global
   std::vector<__nv_bfloat16> A(RT * K), B(N * K);
   std::vector<float> Af(RT * K), Bf(N * K);
@@ -116,14 +122,15 @@ int main(int argc, char** argv) {
   CK(cudaMemset(dD, 0, 256 * N * 4));
   CK(cudaFuncSetAttribute(probe2, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
   for (int it = 0; it < (rate ? 2 : 1); ++it) {
-    probe2<<<grid, 128, 65536>>>(dA, dB, dD, N, shift, rate, dC);
+    probe2<<<grid, 128, 65536>>>(dA, dB, dD, N, shift, rate, dC, commit_every);
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());
   }
   if (rate) {
     long long c;
     CK(cudaMemcpy(&c, dC, 8, cudaMemcpyDeviceToHost));
-    printf("cta_group::2 M=256 N=%d grid=%d: %.1f cycles/MMA (1-CTA equivalent work: 2 x (128 x %d))\n", N, grid, (double)c / REP, N);
+    printf("cta_group::2 M=256 N=%d grid=%d commit_every=%d: %.1f cycles/MMA (1-CTA equivalent work: 2 x (128 x %d))\n", N, grid,
+           commit_every, (double)c / REP, N);
     return 0;
   }
   std::vector<float> D(256 * N);
