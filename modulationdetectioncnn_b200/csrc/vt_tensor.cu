@@ -156,7 +156,8 @@ template <bool TF32>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ConvCfg<TF32>::kThreads, 1)
 vt_conv_kernel(const __grid_constant__ ConvW1 w1c, const float* __restrict__ x, long long n,
                const float* __restrict__ b2g, const uint8_t* __restrict__ w2img,
-               void* __restrict__ act0, void* __restrict__ act1, long long num_st, int dbg_rt) {
+               void* __restrict__ act0, void* __restrict__ act1, long long num_st, int dbg_rt,
+               long long* __restrict__ trace) {
   using ConvSmem = ConvCfg<TF32>;
   constexpr int kStages = ConvSmem::kStages, kChunks = ConvSmem::kChunks;
   constexpr int kASlot = ConvSmem::kASlot, kBSlot = ConvSmem::kBSlot, kAImg = ConvSmem::kAImg, kBImg = ConvSmem::kBImg;
@@ -169,8 +170,11 @@ vt_conv_kernel(const __grid_constant__ ConvW1 w1c, const float* __restrict__ x, 
   // 4 = epilogue skips TMEM loads / math / stores.  Compiled out of the product build.
 #ifdef MDC_VT_ABLATE
   const int dbg = dbg_rt;
+  // clock64 trace of CTA 0 (ablate builds, MDC_VT_TRACE=file): trace[role * 512 + i]
+#define MDC_TRACE3(role, i) do { if (trace && blockIdx.x == 0 && (i) < 512) trace[(role) * 512 + (i)] = clock64(); } while (0)
 #else
   constexpr int dbg = 0;
+#define MDC_TRACE3(role, i) do { } while (0)
 #endif
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ConvSmem::bars);
@@ -253,12 +257,15 @@ vt_conv_kernel(const __grid_constant__ ConvW1 w1c, const float* __restrict__ x, 
       for (long long base = st_first; base < num_st; base += st_step, ++k) {
         const uint32_t buf = k % kAccBufs, use = k / kAccBufs;
         const uint32_t acc = tmem + buf * kAccCols;
+        if (lane == 0) MDC_TRACE3(1, 2 * k);
         mbar_wait(&tmem_empty[buf], (use & 1) ^ 1);          // both epilogues drained this buffer
         tc_fence_after_sync();
+        if (lane == 0) MDC_TRACE3(1, 2 * k + 1);
         for (int c = 0; c < kChunks; ++c, ++it) {
           const uint32_t s = it % kStages, ph = (it / kStages) & 1;
           mbar_wait(&full[s], ph);               // own producers, own TMA and the peer's relay
           tc_fence_after_sync();
+          if (lane == 0) MDC_TRACE3(0, it);
           if (elect_one()) {
             const uint32_t a_lo = smem_desc_lo(a_base + s * kASlot, kALbo);
             const uint32_t b_lo = smem_desc_lo(b_base + s * kBSlot, kBLbo);
@@ -476,7 +483,9 @@ vt_conv_kernel(const __grid_constant__ ConvW1 w1c, const float* __restrict__ x, 
           if (lane == 0) mbar_arrive(&full[(it - 1) % kStages]);
         }
         const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+        if (pw == 0 && lane == 0) MDC_TRACE3(2, 2 * it);
         mbar_wait(&empty[s], ph ^ 1);
+        if (pw == 0 && lane == 0) MDC_TRACE3(2, 2 * it + 1);
         uint8_t* arow = smem + ConvSmem::a + s * kASlot + row * 16;
         if (!(dbg & 1)) {
 #pragma unroll
@@ -1460,12 +1469,30 @@ int launch_vt_conv(mdc_handle_s* h, const float* x, int64_t m, int64_t frame_off
   const unsigned grid_c = 2u * (unsigned)(pairs_needed < pairs_max ? pairs_needed : pairs_max);
   const float* b2 = reinterpret_cast<const float*>(h->vt_b2.ptr);
   const uint8_t* w2 = reinterpret_cast<const uint8_t*>(h->vt_w2_bf16.ptr);
+  long long* trace3 = nullptr;
+#ifdef MDC_VT_ABLATE
+  static long long* trace3_buf = nullptr;
+  if (!trace3_buf) cudaMalloc(&trace3_buf, 4 * 512 * 8);
+  cudaMemsetAsync(trace3_buf, 0, 4 * 512 * 8, stream);
+  trace3 = trace3_buf;
+#endif
   prof_begin(h, stream);
   if (tf32)
-    vt_conv_kernel<true><<<grid_c, ConvCfg<true>::kThreads, ConvCfg<true>::total, stream>>>(w1c, x, m, b2, w2, act0, act1, num_st, dbg);
+    vt_conv_kernel<true><<<grid_c, ConvCfg<true>::kThreads, ConvCfg<true>::total, stream>>>(w1c, x, m, b2, w2, act0, act1, num_st, dbg, trace3);
   else
-    vt_conv_kernel<false><<<grid_c, ConvCfg<false>::kThreads, ConvCfg<false>::total, stream>>>(w1c, x, m, b2, w2, act0, act1, num_st, dbg);
+    vt_conv_kernel<false><<<grid_c, ConvCfg<false>::kThreads, ConvCfg<false>::total, stream>>>(w1c, x, m, b2, w2, act0, act1, num_st, dbg, trace3);
   prof_end(h, stream);
+#ifdef MDC_VT_ABLATE
+  if (trace3 && getenv("MDC_VT_TRACE")) {
+    std::vector<long long> t(4 * 512);
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(t.data(), trace3, t.size() * 8, cudaMemcpyDeviceToHost);
+    if (FILE* f = fopen(getenv("MDC_VT_TRACE"), "w")) {
+      for (size_t i = 0; i < t.size(); ++i) fprintf(f, "%zu %lld\n", i, t[i]);
+      fclose(f);
+    }
+  }
+#endif
   h->launches += 1;
   MDC_CUDA(cudaGetLastError());
   return MDC_OK;
