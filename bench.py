@@ -428,6 +428,14 @@ def other_paths(torch, dev, peaks, _lib):
             1036, n, UNIT, peaks, torch, h2d=nh * 1024, d2h=nh * 12,
             extra={"dtype": "f32", "flop_per_frame": flop,
                    "fp32_fma_ceiling_frames_per_s": 148 * 128 * 2 * 1.965e9 / flop}, host_units=nh))
+    # BASELINE configs[1] names the F=10 checkpoint file at batch 65,536: the same kernel at that batch size, one launch
+    # per step over 32 rotating 64 MiB slices of the 2 GiB input (slices > L2 apart)
+    nb = 65536
+    out.append(hbm_path(
+        "tiny_f32 F=10, batch 65,536 per launch (configs[1] checkpoint file convmodrecnets_CNN2_0.5.wts.h5)", tm,
+        lambda i: _lib.check(tm._h._lib.mdc_predict_f32(tm._h.ptr, xf[(i % 32) * nb:].data_ptr(), nb, pf.data_ptr(), None, None, None, stream)),
+        None, 1036, nb, UNIT, peaks, torch, steps=32, warmup=4,
+        extra={"dtype": "f32", "flop_per_frame": 25800, "fp32_fma_ceiling_frames_per_s": 148 * 128 * 2 * 1.965e9 / 25800}))
     del xf, pf
 
     # 8f-4: raw RTL-SDR ingest, 2^28 samples (512 MiB of u8 in, 2 GiB f32 + 2 GiB Q6.12 frames out)
