@@ -6,15 +6,14 @@
 //   y[r][p][f] = relu(xp[r][p]*k0[f] + xp[r][p+1]*k1[f] + b[f]),  p = 0..128, xp[0]=xp[129]=0
 //   z[c]       = relu(sum_{r,p,f} y[r][p][f] * D[(r*129 + p)*F + f][c] + d[c])
 //
-// HBM-bound (1,036 B per frame), so the kernel is built around keeping bytes in flight: persistent
-// CTAs, one producer warp streaming blocks of 8R frames into a shared-memory ring with 1-D bulk
-// TMA copies (mbarrier full/empty per stage, ~100 KB in flight per CTA), eight consumer warps
-// taking R frames each per stage.  A consumer warp maps lane l to positions p = 4l..4l+3 of both
-// rows (conflict-free 16-B shared loads); position 128 (which only needs x[127]) is spread over
-// lanes 0..2F-1, one (row,filter) pair each.  The math is packed FFMA2 (two positions per
-// instruction).  For F*C small enough (F=3,C=3: 72 registers) the Dense rows a lane needs stay in
-// registers for the whole kernel; otherwise they live in shared memory.  Softmax, argmax and the
-// class histogram are fused in the epilogue.
+// 1,036 B per frame.  A consumer warp maps lane l to positions p = 4l..4l+3 of both rows (16-B loads); position
+// 128 (which only needs x[127]) is spread over lanes 0..2F-1, one (row,filter) pair each.  The math is packed
+// FFMA2 (two positions per instruction), the Dense rows a lane needs live in shared memory (or, F=3 variant 0, in
+// registers), and the epilogue - cross-lane sums by recursive halving, softmax, argmax, class histogram - is
+// fused.  Two ways to feed the warps (template parameter STAGES): the default "direct" form (STAGES = 0: every
+// warp fetches its own R frames one block ahead with streaming 16-B loads) and a TMA ring (one producer warp
+// streaming blocks of 7R frames into shared memory with 1-D bulk copies, mbarrier full/empty per stage); see the
+// measurements at the launch site.
 #include "mdc_internal.cuh"
 #include "sm100.cuh"
 
@@ -59,7 +58,11 @@ tiny_f32_kernel(const TinyParams p, const float4* __restrict__ dmain, const floa
                 const float* __restrict__ x, long long n, float* __restrict__ probs,
                 float* __restrict__ dense, int* __restrict__ cls,
                 unsigned long long* __restrict__ hist) {
-  constexpr int kBlockFrames = kTinyConsumers * R;
+  // STAGES == 0: "direct" variant - no ring and no producer: all eight warps are consumers and fetch their own
+  // frames from global memory, one block ahead (for compute-bound shapes: warps are not coupled through a ring)
+  constexpr bool kDirect = STAGES == 0;
+  constexpr int kCons = kDirect ? kTinyConsumers + 1 : kTinyConsumers;
+  constexpr int kBlockFrames = kCons * R;
   constexpr int kStageBytes = kBlockFrames * 1024;
   constexpr int kWBytes = WREG ? 0 : 2 * F * C * 128 * 4;
   extern __shared__ __align__(128) uint8_t smem[];
@@ -85,11 +88,11 @@ tiny_f32_kernel(const TinyParams p, const float4* __restrict__ dmain, const floa
   }
   __syncthreads();
 
-  if (warp == kTinyConsumers) {
+  if (!kDirect && warp == kTinyConsumers) {
     // ---- producer: one bulk copy per block of frames
     uint32_t it = 0;
     for (long long blk = blockIdx.x; blk < nblocks; blk += gridDim.x, ++it) {
-      const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+      const uint32_t s = it % (kDirect ? 1 : STAGES), ph = (it / (kDirect ? 1 : STAGES)) & 1;
       const long long f0 = blk * kBlockFrames;
       const long long left = n - f0;
       const uint32_t bytes = (uint32_t)(left < kBlockFrames ? left : kBlockFrames) * 1024u;
@@ -125,21 +128,42 @@ tiny_f32_kernel(const TinyParams p, const float4* __restrict__ dmain, const floa
   unsigned cnt = 0;
 
   uint32_t it = 0;
+  float4 nxi[kDirect ? R : 1], nxq[kDirect ? R : 1];
+  auto fetch = [&](long long blk) {               // direct variant: this warp's R frames of block blk
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const long long f = blk * kBlockFrames + warp * R + r;
+      if (kDirect && blk < nblocks && f < n) {
+        asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                     : "=f"(nxi[r].x), "=f"(nxi[r].y), "=f"(nxi[r].z), "=f"(nxi[r].w) : "l"(x4 + f * 64 + lane));
+        asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                     : "=f"(nxq[r].x), "=f"(nxq[r].y), "=f"(nxq[r].z), "=f"(nxq[r].w) : "l"(x4 + f * 64 + 32 + lane));
+      } else if (kDirect) {
+        nxi[r] = nxq[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+  };
+  if (kDirect) fetch(blockIdx.x);
   for (long long blk = blockIdx.x; blk < nblocks; blk += gridDim.x, ++it) {
-    const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
     const long long f0 = blk * kBlockFrames + warp * R;
-    mbar_wait(&full[s], ph);
     float4 xi[R], xq[R];
-    {
+    if (kDirect) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) { xi[r] = nxi[r]; xq[r] = nxq[r]; }
+      fetch(blk + gridDim.x);
+    } else {
+      const uint32_t s = it % (kDirect ? 1 : STAGES), ph = (it / (kDirect ? 1 : STAGES)) & 1;
+      mbar_wait(&full[s], ph);
       const float4* src = reinterpret_cast<const float4*>(ring + s * kStageBytes) + warp * R * 64;
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         xi[r] = src[r * 64 + lane];
         xq[r] = src[r * 64 + 32 + lane];
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);       // frames are in registers: hand the stage back
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&empty[s]);       // frames are in registers: hand the stage back
 
     uint64_t acc[R][C];       // {even positions, odd positions} partial sums
     uint64_t PI01[R], PI23[R], XI01[R], XI23[R], PQ01[R], PQ23[R], XQ01[R], XQ23[R];
@@ -425,12 +449,17 @@ int launch_tiny_f32(mdc_handle_s* h, const float* x, int64_t n, float* probs, fl
     long long max_blocks = (long long)h->num_sms * 2 * 4;
     return (unsigned)(blocks > max_blocks ? max_blocks : blocks);
   };
-  // variant selection (MDC_TINY_VARIANT, tuning aid): 1 (default) = Dense rows in shared memory,
-  // 3 CTAs/SM; 0 = Dense rows in registers (F=3) / 2 CTAs/SM.  Measured on B200 (2^21 frames):
-  // F=3: 2.63e9 vs 2.55e9 frames/s, F=10: 1.25e9 vs 1.21e9.
-  static const int variant = getenv("MDC_TINY_VARIANT") ? atoi(getenv("MDC_TINY_VARIANT")) : 1;
-  auto ring_grid = [&](int R, int ctas_per_sm) {
-    const long long nblocks = (n + kTinyConsumers * R - 1) / (kTinyConsumers * R);
+  // variant selection (MDC_TINY_VARIANT, tuning aid).  Measured on B200, 2^21 frames, frames/s:
+  //   3 (default) direct loads, no ring, 8 consumer warps, 2 CTAs/SM     F=3: 3.42e9   F=10: 1.51e9
+  //   2           direct loads, 3 CTAs/SM (80 registers, small spills)   F=3: 3.39e9   F=10: 1.45e9
+  //   1           TMA ring, Dense rows in shared memory, 3 CTAs/SM       F=3: 3.14e9   F=10: 1.32e9
+  //   0           TMA ring, Dense rows in registers (F=3) / 2 CTAs/SM    F=3: 2.55e9   F=10: 1.21e9
+  // The ring keeps more bytes in flight, but these kernels are issue-bound, not latency-bound, and the ring couples
+  // the consumer warps of a CTA (a stage is refilled only when the slowest of seven warps has taken its frames:
+  // 15 % of the consumers' samples sat in the full-barrier wait) and spends a warp on the producer.
+  static const int variant = getenv("MDC_TINY_VARIANT") ? atoi(getenv("MDC_TINY_VARIANT")) : 3;
+  auto ring_grid = [&](int R, int ctas_per_sm, int cons = kTinyConsumers) {
+    const long long nblocks = (n + cons * R - 1) / (cons * R);
     const long long max_blocks = (long long)h->num_sms * ctas_per_sm;
     return (unsigned)(nblocks > max_blocks ? max_blocks : nblocks);
   };
@@ -443,15 +472,20 @@ int launch_tiny_f32(mdc_handle_s* h, const float* x, int64_t n, float* probs, fl
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, smem_));                   \
       attr_ = true;                                                                                         \
     }                                                                                                       \
-    tiny_f32_kernel<F_, C_, R_, S_, WREG_, MINB_><<<ring_grid(R_, MINB_), kTinyThreads, smem_, stream>>>(   \
+    tiny_f32_kernel<F_, C_, R_, S_, WREG_, MINB_><<<ring_grid(R_, MINB_, S_ == 0 ? kTinyConsumers + 1 : kTinyConsumers),     \
+                                                    kTinyThreads, smem_, stream>>>(                         \
         p, dm, dt, x, n, probs, dense, cls, hist);                                                          \
   } while (0)
   prof_begin(h, stream);
   if (F == 3 && C == 3) {
-    if (variant == 1) MDC_TINY_LAUNCH(3, 3, 2, 4, false, 3);
+    if (variant == 3) MDC_TINY_LAUNCH(3, 3, 2, 0, false, 2);
+    else if (variant == 2) MDC_TINY_LAUNCH(3, 3, 2, 0, false, 3);
+    else if (variant == 1) MDC_TINY_LAUNCH(3, 3, 2, 4, false, 3);
     else MDC_TINY_LAUNCH(3, 3, 1, 12, true, 2);
   } else if (F == 10 && C == 3) {
-    if (variant == 1) MDC_TINY_LAUNCH(10, 3, 2, 3, false, 3);
+    if (variant == 3) MDC_TINY_LAUNCH(10, 3, 2, 0, false, 2);
+    else if (variant == 2) MDC_TINY_LAUNCH(10, 3, 2, 0, false, 3);
+    else if (variant == 1) MDC_TINY_LAUNCH(10, 3, 2, 3, false, 3);
     else MDC_TINY_LAUNCH(10, 3, 2, 4, false, 2);
   } else {
     tiny_f32_generic_kernel<<<grid(1), threads, 0, stream>>>(
