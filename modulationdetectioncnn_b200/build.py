@@ -23,8 +23,18 @@ def nvcc() -> str:
     raise RuntimeError("nvcc not found")
 
 
+STAMP = os.path.join(HERE, "build", "flags.txt")
+
+
+def _flag_stamp() -> str:
+    return " ".join(NVCC_FLAGS + os.environ.get("MDC_NVCC_EXTRA", "").split())
+
+
 def needs_build() -> bool:
     if not os.path.exists(LIB):
+        return True
+    # a library built with other flags (e.g. -DMDC_VT_ABLATE for timing experiments) is never reused
+    if not os.path.exists(STAMP) or open(STAMP).read() != _flag_stamp():
         return True
     t = os.path.getmtime(LIB)
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [
@@ -59,6 +69,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     cmd = [nvcc(), "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart_static",
            "-Xcompiler", "-fPIC"]
     subprocess.run(cmd, check=True)
+    with open(STAMP, "w") as fh:
+        fh.write(_flag_stamp())
     return LIB
 
 
