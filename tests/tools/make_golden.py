@@ -3,7 +3,7 @@
 
 Run in the build container (``/root/reference`` present):
 
-    python tools/make_golden.py
+    python tests/tools/make_golden.py
 
 The GPU box has no ``/root/reference``; GPU parity tests, ``smoke()`` and
 ``bench.py`` read only the small fixtures written here.  Everything is
@@ -34,7 +34,7 @@ import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 from modulationdetectioncnn_b200 import svtext  # noqa: E402

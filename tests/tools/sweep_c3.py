@@ -5,7 +5,7 @@ and for the VT-CNN2 stack in its three arithmetic modes, compare the CUDA path w
 synthetic frames: max error of the last Dense output relative to the frame's largest |value|, max |softmax| error,
 argmax agreement.  Test tool: uses oracle/ as the checker.
 
-    python tools/sweep_c3.py [out.md]
+    python tests/tools/sweep_c3.py [out.md]
 """
 import json
 import os
@@ -13,7 +13,7 @@ import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from modulationdetectioncnn_b200 import synth                      # noqa: E402
 from modulationdetectioncnn_b200.model import tiny_cnn2, vt_cnn2    # noqa: E402

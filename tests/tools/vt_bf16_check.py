@@ -1,6 +1,6 @@
 """GPU debugging aid: VT-CNN2 bf16 path, layer by layer, against a bf16-emulating numpy model.
 
-    python tools/vt_bf16_check.py [n_frames]
+    python tests/tools/vt_bf16_check.py [n_frames]
 
 Uses oracle/ only as the checker (this is a test tool, not a product path).
 """
@@ -10,7 +10,7 @@ import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 from modulationdetectioncnn_b200 import _lib, synth          # noqa: E402

@@ -5,7 +5,7 @@ import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from modulationdetectioncnn_b200 import _lib, synth          # noqa: E402
 from modulationdetectioncnn_b200.model import vt_cnn2          # noqa: E402
