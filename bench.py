@@ -249,6 +249,8 @@ def run_ours(args):
         init_process_group("nccl")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    from modulationdetectioncnn_b200.dist import bind_to_gpu_numa_node
+    numa_node = bind_to_gpu_numa_node(local) if dist_on else None      # host buffers next to their GPU
     peaks = load_peaks()
 
     # ---------------- headline: VT-CNN2 (C2b), batch 65536 per GPU
@@ -347,7 +349,8 @@ def run_ours(args):
                    "precision": "headline = the bf16 fast mode BASELINE's north_star defines; the fp32-accurate modes "
                                 "(tf32x3 on tensor cores, fp32 on CUDA cores) are timed in the same run under 'modes'",
                    "l2": f"{N_INPUT_BUFFERS} distinct input buffers rotated ({N_INPUT_BUFFERS * batch * 1024 >> 20} MiB > 126 MB L2)",
-                   "parallelism": f"frame-sharded dp{world}, one NCCL all-reduce of int64[11] histogram"},
+                   "parallelism": f"frame-sharded dp{world}, one NCCL all-reduce of int64[11] histogram",
+                   "numa_node_of_rank0": numa_node},
         "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk.summary(),
     }
 

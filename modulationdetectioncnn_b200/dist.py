@@ -12,7 +12,7 @@ from typing import Tuple
 
 import numpy as np
 
-__all__ = ["shard_range", "init_process_group", "allreduce_histogram", "rank_world"]
+__all__ = ["shard_range", "init_process_group", "allreduce_histogram", "rank_world", "bind_to_gpu_numa_node"]
 
 
 def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
@@ -59,3 +59,37 @@ def allreduce_histogram(hist):
         t = t.cuda()
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return t.cpu().numpy()
+
+
+def _parse_cpulist(text: str):
+    cpus = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.extend(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa_node(device: int = 0):
+    """Pin this process (and, by first touch, the host buffers it allocates afterwards) to the NUMA node the GPU
+    hangs off.  With one rank per GPU streaming ~50 GB/s of frames each, pinned buffers that land on the other
+    socket put every copy on the inter-socket link.  Returns the node, or None when the topology is not exposed
+    (no sysfs entry, single node) - binding is an optimisation, never a requirement."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(device).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(device), "pci_domain_id", 0)
+        dev = getattr(torch.cuda.get_device_properties(device), "pci_device_id", 0)
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node"
+        node = int(open(path).read())
+        if node < 0:
+            return None
+        cpus = set(_parse_cpulist(open(f"/sys/devices/system/node/node{node}/cpulist").read()))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None

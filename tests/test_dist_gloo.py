@@ -62,3 +62,10 @@ def test_histogram_allreduce_world2():
     x = np.trunc(np.random.Generator(np.random.Philox(2015)).normal(0, 32, (n, 256))).astype(np.int32)
     full = np.bincount(sv.forward(x, g["A_conv_tab"], g["A_dense_bias"], g["A_dense_tabs"]).argmax(-1), minlength=3)
     assert full.tolist() == total.tolist()               # sharded == unsharded
+
+
+def test_cpulist_parser_and_numa_binding_is_optional():
+    from modulationdetectioncnn_b200.dist import _parse_cpulist, bind_to_gpu_numa_node
+    assert _parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    assert _parse_cpulist("") == []
+    assert bind_to_gpu_numa_node(0) is None or isinstance(bind_to_gpu_numa_node(0), int)    # no GPU here: None, no error
