@@ -120,6 +120,15 @@ MDC_API int mdc_predict_f32_host(mdc_handle_t h, const float* x_host, int64_t n,
                                  float* dense_host, int32_t* cls_host,
                                  unsigned long long* hist_host);
 
+/* Streaming form of the call above: returns as soon as the copies and kernels are enqueued, so the next batch's
+ * transfer runs under this batch's kernels.  All host buffers must stay valid (and should be pinned) until
+ * mdc_host_wait(h, *ticket) returns; results of successive calls complete in issue order.  Handles whose path has
+ * no internal pipeline (TinyCNN2, VT-CNN2 fp32 mode) run the call synchronously and return ticket 0.            */
+MDC_API int mdc_predict_f32_host_async(mdc_handle_t h, const float* x_host, int64_t n, float* probs_host,
+                                       float* dense_host, int32_t* cls_host,
+                                       unsigned long long* hist_host, int64_t* ticket);
+MDC_API int mdc_host_wait(mdc_handle_t h, int64_t ticket);
+
 /* ---- integer (SystemVerilog-exact) inference ------------------------------------------
  * Replaces: one reset-to-done run of `layers_top` (cnn_test_latest1.sv:144-209) per frame,
  * fed by `test_input`/`test_table` (:71-142).

@@ -56,6 +56,11 @@ struct HostPipe {
   cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr;
   cudaEvent_t e_h2d[kSlots] = {}, e_comp[kSlots] = {}, e_d2h[kSlots] = {};
   cudaEvent_t e_pass[2] = {}, e_pass_d2h[2] = {};      // tensor-core VT path: per-pass output buffers
+  // asynchronous calls: slot / pass counters run on across calls (a later call's first chunks must not overwrite
+  // slots an earlier call's tail still reads), one completion event per call
+  static constexpr int kTickets = 16;
+  int64_t chunk_seq = 0, pass_seq = 0, ticket_seq = 0;
+  cudaEvent_t e_ticket[kTickets] = {}, e_hist = nullptr;
   DeviceBuffer x[kSlots], o0[kSlots], o1[kSlots], o2[kSlots];
   DeviceBuffer hist;
   int init() {
@@ -72,6 +77,8 @@ struct HostPipe {
       MDC_CUDA(cudaEventCreateWithFlags(&e_pass[i], cudaEventDisableTiming));
       MDC_CUDA(cudaEventCreateWithFlags(&e_pass_d2h[i], cudaEventDisableTiming));
     }
+    for (int i = 0; i < kTickets; ++i) MDC_CUDA(cudaEventCreateWithFlags(&e_ticket[i], cudaEventDisableTiming));
+    MDC_CUDA(cudaEventCreateWithFlags(&e_hist, cudaEventDisableTiming));
     return hist.reserve(kMaxClasses * kMaxClasses * sizeof(unsigned long long));
   }
   void destroy() {
@@ -82,6 +89,8 @@ struct HostPipe {
       x[i].release(); o0[i].release(); o1[i].release(); o2[i].release();
     }
     for (int i = 0; i < 2; ++i) { cudaEventDestroy(e_pass[i]); cudaEventDestroy(e_pass_d2h[i]); }
+    for (int i = 0; i < kTickets; ++i) cudaEventDestroy(e_ticket[i]);
+    cudaEventDestroy(e_hist);
     hist.release();
     cudaStreamDestroy(s_h2d); cudaStreamDestroy(s_comp); cudaStreamDestroy(s_d2h);
     s_h2d = nullptr;
@@ -201,8 +210,10 @@ static int run_host_pipeline(mdc_handle_s* h, const In* x, int64_t n, O0* o0, O1
 // first convolution starts early and every later copy hides under the previous chunk's convolution; dense1
 // and the head run ONCE per pass over all the activations (a dense tile is 256 frames per SM: per-chunk
 // launches would leave most SMs idle), and the pass's results are copied back under the next pass.
+// ticket == NULL: synchronous (returns with the outputs in host memory); otherwise returns after enqueueing and
+// *ticket names the completion event (mdc_host_wait)
 static int run_vt_host_pipeline(mdc_handle_s* h, const float* x, int64_t n, float* probs, float* dense, int32_t* cls,
-                                unsigned long long* hist) {
+                                unsigned long long* hist, int64_t* ticket) {
   if (!h->pipe) h->pipe = new HostPipe();
   HostPipe& P = *h->pipe;
   if (int e = P.init()) return e;
@@ -227,7 +238,8 @@ static int run_vt_host_pipeline(mdc_handle_s* h, const float* x, int64_t n, floa
     if (dense) if (int e = P.o1[b].reserve((size_t)cap * C * sizeof(float))) return e;
     if (cls) if (int e = P.o2[b].reserve((size_t)cap * sizeof(int32_t))) return e;
   }
-  int64_t i = 0, pi = 0;
+  int64_t& i = P.chunk_seq;
+  int64_t& pi = P.pass_seq;
   for (int64_t p0 = 0; p0 < n; p0 += pass, ++pi) {
     const int64_t pm = (n - p0) < pass ? (n - p0) : pass;
     const int ob = (int)(pi & 1);
@@ -236,7 +248,7 @@ static int run_vt_host_pipeline(mdc_handle_s* h, const float* x, int64_t n, floa
       // the very first chunk is small (2 MiB): nothing can overlap its copy
       step = (p0 == 0 && c0 == 0 && !tf32 && pm > 2 * env_first) ? env_first : chunk;
       const int64_t m = (pm - c0) < step ? (pm - c0) : step;
-      if (i >= S) MDC_CUDA(cudaStreamWaitEvent(P.s_h2d, P.e_comp[k], 0));
+      MDC_CUDA(cudaStreamWaitEvent(P.s_h2d, P.e_comp[k], 0));     // (a never-recorded event does not block)
       MDC_CUDA(cudaMemcpyAsync(P.x[k].ptr, x + (p0 + c0) * kFrameElems, (size_t)m * kFrameElems * sizeof(float),
                                cudaMemcpyHostToDevice, P.s_h2d));
       MDC_CUDA(cudaEventRecord(P.e_h2d[k], P.s_h2d));
@@ -244,7 +256,7 @@ static int run_vt_host_pipeline(mdc_handle_s* h, const float* x, int64_t n, floa
       if (int e = launch_vt_conv(h, (const float*)P.x[k].ptr, m, c0, P.s_comp)) return e;
       MDC_CUDA(cudaEventRecord(P.e_comp[k], P.s_comp));
     }
-    if (pi >= 2) MDC_CUDA(cudaStreamWaitEvent(P.s_comp, P.e_pass_d2h[ob], 0));
+    MDC_CUDA(cudaStreamWaitEvent(P.s_comp, P.e_pass_d2h[ob], 0));
     if (int e = launch_vt_dense_head(h, pm, probs ? (float*)P.o0[ob].ptr : nullptr, dense ? (float*)P.o1[ob].ptr : nullptr,
                                      cls ? (int32_t*)P.o2[ob].ptr : nullptr,
                                      hist ? (unsigned long long*)P.hist.ptr : nullptr, P.s_comp))
@@ -257,11 +269,18 @@ static int run_vt_host_pipeline(mdc_handle_s* h, const float* x, int64_t n, floa
     MDC_CUDA(cudaEventRecord(P.e_pass_d2h[ob], P.s_d2h));
   }
   if (hist) {
-    MDC_CUDA(cudaStreamSynchronize(P.s_comp));
-    MDC_CUDA(cudaMemcpyAsync(hist, P.hist.ptr, C * sizeof(unsigned long long), cudaMemcpyDeviceToHost, P.s_d2h));
+    // on the compute stream: after this call's last dense1 launch, before the next call's memset
+    MDC_CUDA(cudaMemcpyAsync(hist, P.hist.ptr, C * sizeof(unsigned long long), cudaMemcpyDeviceToHost, P.s_comp));
+    MDC_CUDA(cudaEventRecord(P.e_hist, P.s_comp));
+    MDC_CUDA(cudaStreamWaitEvent(P.s_d2h, P.e_hist, 0));
   }
-  MDC_CUDA(cudaStreamSynchronize(P.s_d2h));
-  MDC_CUDA(cudaStreamSynchronize(P.s_comp));
+  const int64_t t = ++P.ticket_seq;
+  MDC_CUDA(cudaEventRecord(P.e_ticket[t % HostPipe::kTickets], P.s_d2h));
+  if (ticket) {
+    *ticket = t;
+    return MDC_OK;
+  }
+  MDC_CUDA(cudaEventSynchronize(P.e_ticket[t % HostPipe::kTickets]));
   return MDC_OK;
 }
 
@@ -467,13 +486,37 @@ int mdc_predict_f32_host(mdc_handle_t h, const float* x_host, int64_t n, float* 
     return MDC_OK;
   }
   if (h->model == MDC_MODEL_VT && h->mode != MDC_MODE_FP32)
-    return run_vt_host_pipeline(h, x_host, n, probs_host, dense_host, cls_host, hist_host);
+    return run_vt_host_pipeline(h, x_host, n, probs_host, dense_host, cls_host, hist_host, nullptr);
   const int64_t chunk = 16384;
   return run_host_pipeline<float, float, float>(
       h, x_host, n, probs_host, dense_host, cls_host, hist_host, chunk,
       [h](const float* x, int64_t m, float* p, float* d, int32_t* c, unsigned long long* hs, cudaStream_t s) {
         return predict_f32_dev(h, x, m, p, d, c, hs, s);
       });
+}
+
+int mdc_predict_f32_host_async(mdc_handle_t h, const float* x_host, int64_t n, float* probs_host, float* dense_host,
+                               int32_t* cls_host, unsigned long long* hist_host, int64_t* ticket) {
+  MDC_REQUIRE(ticket != nullptr, MDC_ERR_INVALID, "ticket is NULL");
+  *ticket = 0;                                   // 0: nothing pending (the call below was synchronous)
+  MDC_CHECK_HANDLE(h);
+  if (h->model == MDC_MODEL_VT && h->mode != MDC_MODE_FP32 && n > 0) {
+    MDC_REQUIRE(x_host != nullptr, MDC_ERR_INVALID, "x_host is NULL");
+    if (int e = ensure_packed(h)) return e;
+    return run_vt_host_pipeline(h, x_host, n, probs_host, dense_host, cls_host, hist_host, ticket);
+  }
+  return mdc_predict_f32_host(h, x_host, n, probs_host, dense_host, cls_host, hist_host);
+}
+
+int mdc_host_wait(mdc_handle_t h, int64_t ticket) {
+  MDC_CHECK_HANDLE(h);
+  if (ticket <= 0 || !h->pipe) return MDC_OK;
+  HostPipe& P = *h->pipe;
+  MDC_REQUIRE(ticket <= P.ticket_seq, MDC_ERR_INVALID, "ticket %lld was never issued", (long long)ticket);
+  // completion events fire in issue order; a ticket whose event slot has been reused is covered by the newest one
+  const int64_t t = (P.ticket_seq - ticket >= HostPipe::kTickets) ? P.ticket_seq : ticket;
+  MDC_CUDA(cudaEventSynchronize(P.e_ticket[t % HostPipe::kTickets]));
+  return MDC_OK;
 }
 
 int mdc_predict_q612_host(mdc_handle_t h, const int32_t* x_host, int64_t n, int32_t* out_host, int32_t* pre_host,

@@ -28,7 +28,7 @@ import numpy as np
 from . import _lib
 from .h5lite import H5File
 
-__all__ = ["CNN2Model", "tiny_cnn2", "vt_cnn2", "load_model", "read_keras_weights"]
+__all__ = ["CNN2Model", "PendingPrediction", "tiny_cnn2", "vt_cnn2", "load_model", "read_keras_weights"]
 
 _MODES = {"fp32": _lib.MODE_FP32, "bf16": _lib.MODE_BF16, "tf32x3": _lib.MODE_TF32X3}
 
@@ -164,6 +164,27 @@ class CNN2Model:
             return self._run(x, False, False, True, False)["cls"]
         raise ValueError("output must be 'softmax', 'dense' or 'argmax'")
 
+    def predict_async(self, x, output: str = "softmax") -> "PendingPrediction":
+        """Streaming form of :meth:`predict` for host (numpy) batches: returns at once, the next batch's transfer
+        then runs under this batch's kernels; ``.result()`` waits for and returns this batch's array.  ``x`` must
+        stay unchanged until then and should be pinned (``torch.from_numpy(a).pin_memory().numpy()``); results
+        complete in submission order.  (Keras' ``predict`` has no counterpart: it is the call for a stream of
+        batches, e.g. from ``sdr.ingest_u8``.)"""
+        key = {"softmax": "probs", "dense": "dense", "argmax": "cls"}.get(output)
+        if key is None:
+            raise ValueError("output must be 'softmax', 'dense' or 'argmax'")
+        if _is_torch(x):
+            raise ValueError("predict_async takes host (numpy) batches; CUDA tensors are already asynchronous")
+        import ctypes as C
+        xa = np.ascontiguousarray(x, dtype=np.float32).reshape(-1, 256)
+        n, Cn = xa.shape[0], self.classes
+        out = np.empty((n,), dtype=np.int32) if key == "cls" else np.empty((n, Cn), dtype=np.float32)
+        ptr = lambda k: out.ctypes.data if k == key else None  # noqa: E731
+        ticket = C.c_int64(0)
+        _lib.check(self._h._lib.mdc_predict_f32_host_async(self._h.ptr, xa.ctypes.data, n, ptr("probs"), ptr("dense"),
+                                                           ptr("cls"), None, C.byref(ticket)))
+        return PendingPrediction(self, ticket.value, out, xa)
+
     def predict_classes(self, x):
         return self.predict(x, output="argmax")
 
@@ -209,6 +230,19 @@ class CNN2Model:
 
     def close(self) -> None:
         self._h.close()
+
+
+class PendingPrediction:
+    """Handle of one :meth:`CNN2Model.predict_async` batch."""
+
+    def __init__(self, model: CNN2Model, ticket: int, out: np.ndarray, keep_alive):
+        self._model, self._ticket, self._out, self._keep = model, ticket, out, keep_alive
+
+    def result(self) -> np.ndarray:
+        if self._ticket is not None:
+            _lib.check(self._model._h._lib.mdc_host_wait(self._model._h.ptr, self._ticket))
+            self._ticket, self._keep = None, None
+        return self._out
 
 
 def tiny_cnn2(filters: int = 3, classes: int = 3, device: int = 0) -> CNN2Model:

@@ -143,3 +143,37 @@ def test_host_and_device_paths_agree_across_pass_boundaries(vt):
     assert np.array_equal(zh, zd)
     assert np.array_equal(zh[:300], zh[300:600])          # the same frames give the same rows wherever they sit
     assert int(m.class_histogram(xx).sum()) == n
+
+
+@pytest.mark.parametrize("mode", ["bf16", "tf32x3"])
+def test_predict_async_stream_matches_sync(vt, mode):
+    """Several host batches in flight (the next one's copies run under this one's kernels): every result equals the
+    synchronous call's, in submission order, for ragged batch sizes around the chunk / pass boundaries."""
+    import torch
+    from modulationdetectioncnn_b200.model import vt_cnn2
+    w, x, _ = vt
+    m = vt_cnn2(11, mode=mode)
+    m.set_weights(_wlist(w))
+    sizes = [300, 8192 + 5, 1, 2048, 33000] if mode == "bf16" else [300, 1, 19000]
+    batches = []
+    for i, n in enumerate(sizes):
+        b = np.tile(x, (n // x.shape[0] + 1, 1, 1))[:n] * (1.0 + 0.25 * i)
+        batches.append(torch.from_numpy(b.astype(np.float32)).pin_memory().numpy())
+    want = [m.predict(b, output="dense") for b in batches]
+    pend = [m.predict_async(b, output="dense") for b in batches]          # all submitted before any wait
+    for p, wnt in zip(pend, want):
+        assert np.array_equal(p.result(), wnt)
+    # interleaved submit / wait, other outputs, and a second result() call
+    p0 = m.predict_async(batches[0])
+    p1 = m.predict_async(batches[1], output="argmax")
+    assert np.array_equal(p0.result(), m.predict(batches[0])) and np.array_equal(p0.result(), m.predict(batches[0]))
+    assert np.array_equal(p1.result(), want[1].argmax(-1))
+
+
+def test_predict_async_on_unpipelined_models_is_synchronous(h5w):
+    from modulationdetectioncnn_b200 import synth
+    from modulationdetectioncnn_b200.model import tiny_cnn2
+    m = tiny_cnn2(3, 3)
+    m.set_weights(h5w["A_3conv"])
+    x = synth.iq_frames(1000)
+    assert np.array_equal(m.predict_async(x).result(), m.predict(x))

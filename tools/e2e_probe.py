@@ -50,3 +50,22 @@ for _ in range(10):
     _lib.check(lib.mdc_predict_f32(h.ptr, xdev.data_ptr(), n, pd.data_ptr(), None, None, None, stream))
 torch.cuda.synchronize()
 print(f"predict_f32 device: {(time.perf_counter() - t) / 10 * 1e3:.3f} ms")
+
+# streaming form: two calls in flight
+import ctypes as C
+xs = [torch.randn((n, 2, 128)).mul_(2.0 ** -7).pin_memory().numpy() for _ in range(2)]
+ps = [torch.empty((n, 11)).pin_memory().numpy() for _ in range(2)]
+def stream(k):
+    pend = None
+    for i in range(k):
+        t = C.c_int64(0)
+        _lib.check(lib.mdc_predict_f32_host_async(h.ptr, xs[i % 2].ctypes.data, n, ps[i % 2].ctypes.data, None, None, None, C.byref(t)))
+        if pend is not None:
+            _lib.check(lib.mdc_host_wait(h.ptr, pend))
+        pend = t.value
+    _lib.check(lib.mdc_host_wait(h.ptr, pend))
+stream(4)
+t = time.perf_counter()
+stream(20)
+dt = (time.perf_counter() - t) / 20
+print(f"predict_f32_host_async stream: {dt * 1e3:.3f} ms  {n / dt:.4g} frames/s")
