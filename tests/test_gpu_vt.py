@@ -177,3 +177,37 @@ def test_predict_async_on_unpipelined_models_is_synchronous(h5w):
     m.set_weights(h5w["A_3conv"])
     x = synth.iq_frames(1000)
     assert np.array_equal(m.predict_async(x).result(), m.predict(x))
+
+
+def test_device_predict_is_cuda_graph_capturable(vt):
+    """The device-pointer call only enqueues kernels on the caller's stream (no allocation, copy or synchronisation
+    after the first call has sized the work space), so a caller can capture it in a CUDA graph and replay it."""
+    import torch
+    from modulationdetectioncnn_b200 import _lib
+    from modulationdetectioncnn_b200.model import vt_cnn2
+    w, x, _ = vt
+    m = vt_cnn2(11, mode="bf16")
+    m.set_weights(_wlist(w))
+    xd = torch.from_numpy(x).cuda()
+    out = torch.empty((x.shape[0], 11), device="cuda")
+    hist = torch.zeros(11, dtype=torch.int64, device="cuda")
+    lib, h = m._h._lib, m._h
+
+    def call(stream):
+        _lib.check(lib.mdc_predict_f32(h.ptr, xd.data_ptr(), x.shape[0], None, out.data_ptr(), None, hist.data_ptr(), stream))
+
+    call(torch.cuda.current_stream().cuda_stream)          # sizes the work space, sets kernel attributes
+    torch.cuda.synchronize()
+    want = out.clone()
+    g = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        with torch.cuda.graph(g, stream=s):
+            call(s.cuda_stream)
+    out.zero_()
+    hist.zero_()
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, want)
+    assert int(hist.sum()) == 3 * x.shape[0]
