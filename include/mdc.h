@@ -122,8 +122,8 @@ MDC_API int mdc_predict_f32_host(mdc_handle_t h, const float* x_host, int64_t n,
 
 /* Streaming form of the call above: returns as soon as the copies and kernels are enqueued, so the next batch's
  * transfer runs under this batch's kernels.  All host buffers must stay valid (and should be pinned) until
- * mdc_host_wait(h, *ticket) returns; results of successive calls complete in issue order.  Handles whose path has
- * no internal pipeline (TinyCNN2, VT-CNN2 fp32 mode) run the call synchronously and return ticket 0.            */
+ * mdc_host_wait(h, *ticket) returns; results of successive calls complete in issue order (ticket 0 = nothing
+ * pending, e.g. n == 0).  mdc_predict_q612_host_async below is the integer counterpart.                          */
 MDC_API int mdc_predict_f32_host_async(mdc_handle_t h, const float* x_host, int64_t n, float* probs_host,
                                        float* dense_host, int32_t* cls_host,
                                        unsigned long long* hist_host, int64_t* ticket);
@@ -143,6 +143,9 @@ MDC_API int mdc_predict_q612(mdc_handle_t h, const int32_t* x_dev, int64_t n, in
 MDC_API int mdc_predict_q612_host(mdc_handle_t h, const int32_t* x_host, int64_t n,
                                   int32_t* out_host, int32_t* pre_host, int32_t* cls_host,
                                   unsigned long long* hist_host);
+MDC_API int mdc_predict_q612_host_async(mdc_handle_t h, const int32_t* x_host, int64_t n,
+                                        int32_t* out_host, int32_t* pre_host, int32_t* cls_host,
+                                        unsigned long long* hist_host, int64_t* ticket);
 
 /* ---- Walsh-Hadamard transform ----------------------------------------------------------
  * Replaces: the FWHT spectrogram stage named in README.md:5 (no code in the reference).

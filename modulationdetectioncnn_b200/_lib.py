@@ -22,7 +22,7 @@ FWHT_NATURAL, FWHT_SEQUENCY = 0, 1
 
 EXPORTS = [
     "mdc_create", "mdc_destroy", "mdc_set_option", "mdc_set_weights_f32", "mdc_set_weights_q612",
-    "mdc_predict_f32", "mdc_predict_f32_host", "mdc_predict_f32_host_async", "mdc_host_wait", "mdc_predict_q612", "mdc_predict_q612_host",
+    "mdc_predict_f32", "mdc_predict_f32_host", "mdc_predict_f32_host_async", "mdc_host_wait", "mdc_predict_q612", "mdc_predict_q612_host_async", "mdc_predict_q612_host",
     "mdc_fwht_i32", "mdc_fwht_i32_host", "mdc_sdr_ingest_u8", "mdc_confusion_i32", "mdc_confusion_grouped_i32", "mdc_last_error", "mdc_version",
     "mdc_launch_count", "mdc_profile_enable", "mdc_profile_read", "mdc_debug_read",
 ]
@@ -59,6 +59,7 @@ def load() -> C.CDLL:
         "mdc_host_wait": (i32, [vp, i64]),
         "mdc_predict_q612": (i32, [vp, vp, i64, vp, vp, vp, vp, vp]),
         "mdc_predict_q612_host": (i32, [vp, vp, i64, vp, vp, vp, vp]),
+        "mdc_predict_q612_host_async": (i32, [vp, vp, i64, vp, vp, vp, vp, C.POINTER(i64)]),
         "mdc_fwht_i32": (i32, [vp, vp, i64, i32, i32, vp]),
         "mdc_fwht_i32_host": (i32, [vp, vp, i64, i32, i32, i32]),
         "mdc_sdr_ingest_u8": (i32, [vp, i64, vp, vp, vp, vp]),

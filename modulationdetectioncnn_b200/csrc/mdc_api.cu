@@ -160,9 +160,12 @@ static int predict_f32_dev(mdc_handle_s* h, const float* x, int64_t n, float* pr
 using namespace mdc;
 
 // ---- host-buffer variants --------------------------------------------------------------
+// ticket == NULL: synchronous (returns with the outputs in host memory); otherwise returns after enqueueing and
+// *ticket names the completion event (mdc_host_wait).  Slot counters run on across calls, so a later call's first
+// chunks wait for the slots an earlier call's tail still uses.
 template <class In, class O0, class O1, class Launch>
 static int run_host_pipeline(mdc_handle_s* h, const In* x, int64_t n, O0* o0, O1* o1, int32_t* cls,
-                             unsigned long long* hist, int64_t chunk, Launch launch) {
+                             unsigned long long* hist, int64_t chunk, int64_t* ticket, Launch launch) {
   if (!h->pipe) h->pipe = new HostPipe();
   HostPipe& P = *h->pipe;
   if (int e = P.init()) return e;
@@ -175,16 +178,16 @@ static int run_host_pipeline(mdc_handle_s* h, const In* x, int64_t n, O0* o0, O1
     if (o1) if (int e = P.o1[k].reserve((size_t)chunk * C * sizeof(O1))) return e;
     if (cls) if (int e = P.o2[k].reserve((size_t)chunk * sizeof(int32_t))) return e;
   }
-  int64_t i = 0;
+  int64_t& i = P.chunk_seq;
   for (int64_t s = 0; s < n; s += chunk, ++i) {
     const int k = (int)(i % S);
     const int64_t m = (n - s) < chunk ? (n - s) : chunk;
-    if (i >= S) MDC_CUDA(cudaStreamWaitEvent(P.s_h2d, P.e_comp[k], 0));
+    MDC_CUDA(cudaStreamWaitEvent(P.s_h2d, P.e_comp[k], 0));        // (a never-recorded event does not block)
     MDC_CUDA(cudaMemcpyAsync(P.x[k].ptr, x + s * kFrameElems, (size_t)m * kFrameElems * sizeof(In),
                              cudaMemcpyHostToDevice, P.s_h2d));
     MDC_CUDA(cudaEventRecord(P.e_h2d[k], P.s_h2d));
     MDC_CUDA(cudaStreamWaitEvent(P.s_comp, P.e_h2d[k], 0));
-    if (i >= S) MDC_CUDA(cudaStreamWaitEvent(P.s_comp, P.e_d2h[k], 0));
+    MDC_CUDA(cudaStreamWaitEvent(P.s_comp, P.e_d2h[k], 0));
     if (int e = launch((const In*)P.x[k].ptr, m, o0 ? (O0*)P.o0[k].ptr : nullptr,
                        o1 ? (O1*)P.o1[k].ptr : nullptr, cls ? (int32_t*)P.o2[k].ptr : nullptr,
                        hist ? (unsigned long long*)P.hist.ptr : nullptr, P.s_comp))
@@ -197,11 +200,18 @@ static int run_host_pipeline(mdc_handle_s* h, const In* x, int64_t n, O0* o0, O1
     MDC_CUDA(cudaEventRecord(P.e_d2h[k], P.s_d2h));
   }
   if (hist) {
-    MDC_CUDA(cudaStreamSynchronize(P.s_comp));
-    MDC_CUDA(cudaMemcpyAsync(hist, P.hist.ptr, C * sizeof(unsigned long long), cudaMemcpyDeviceToHost, P.s_d2h));
+    // on the compute stream: after this call's last kernel, before the next call's memset
+    MDC_CUDA(cudaMemcpyAsync(hist, P.hist.ptr, C * sizeof(unsigned long long), cudaMemcpyDeviceToHost, P.s_comp));
+    MDC_CUDA(cudaEventRecord(P.e_hist, P.s_comp));
+    MDC_CUDA(cudaStreamWaitEvent(P.s_d2h, P.e_hist, 0));
   }
-  MDC_CUDA(cudaStreamSynchronize(P.s_d2h));
-  MDC_CUDA(cudaStreamSynchronize(P.s_comp));
+  const int64_t t = ++P.ticket_seq;
+  MDC_CUDA(cudaEventRecord(P.e_ticket[t % HostPipe::kTickets], P.s_d2h));
+  if (ticket) {
+    *ticket = t;
+    return MDC_OK;
+  }
+  MDC_CUDA(cudaEventSynchronize(P.e_ticket[t % HostPipe::kTickets]));
   return MDC_OK;
 }
 
@@ -482,8 +492,8 @@ int mdc_predict_q612(mdc_handle_t h, const int32_t* x_dev, int64_t n, int32_t* o
   return launch_q612(h, x_dev, n, out_dev, pre_dev, cls_dev, hist_dev, (cudaStream_t)stream);
 }
 
-int mdc_predict_f32_host(mdc_handle_t h, const float* x_host, int64_t n, float* probs_host, float* dense_host,
-                         int32_t* cls_host, unsigned long long* hist_host) {
+static int predict_f32_host_impl(mdc_handle_t h, const float* x_host, int64_t n, float* probs_host, float* dense_host,
+                                 int32_t* cls_host, unsigned long long* hist_host, int64_t* ticket) {
   MDC_CHECK_HANDLE(h);
   MDC_REQUIRE(h->mode != MDC_MODE_Q612, MDC_ERR_INVALID, "Q6.12 handle: use mdc_predict_q612_host");
   MDC_REQUIRE(n >= 0 && (n == 0 || x_host), MDC_ERR_INVALID, "bad x_host / n");
@@ -493,26 +503,50 @@ int mdc_predict_f32_host(mdc_handle_t h, const float* x_host, int64_t n, float* 
     return MDC_OK;
   }
   if (h->model == MDC_MODEL_VT && h->mode != MDC_MODE_FP32)
-    return run_vt_host_pipeline(h, x_host, n, probs_host, dense_host, cls_host, hist_host, nullptr);
+    return run_vt_host_pipeline(h, x_host, n, probs_host, dense_host, cls_host, hist_host, ticket);
   const int64_t chunk = 16384;
   return run_host_pipeline<float, float, float>(
-      h, x_host, n, probs_host, dense_host, cls_host, hist_host, chunk,
+      h, x_host, n, probs_host, dense_host, cls_host, hist_host, chunk, ticket,
       [h](const float* x, int64_t m, float* p, float* d, int32_t* c, unsigned long long* hs, cudaStream_t s) {
         return predict_f32_dev(h, x, m, p, d, c, hs, s);
       });
 }
 
+static int predict_q612_host_impl(mdc_handle_t h, const int32_t* x_host, int64_t n, int32_t* out_host, int32_t* pre_host,
+                                  int32_t* cls_host, unsigned long long* hist_host, int64_t* ticket) {
+  MDC_CHECK_HANDLE(h);
+  MDC_REQUIRE(h->mode == MDC_MODE_Q612, MDC_ERR_INVALID, "handle is not in Q6.12 mode");
+  MDC_REQUIRE(h->have_q, MDC_ERR_NOT_READY, "ROM tables not set (call mdc_set_weights_q612)");
+  MDC_REQUIRE(n >= 0 && (n == 0 || x_host), MDC_ERR_INVALID, "bad x_host / n");
+  if (n == 0) {
+    if (hist_host) memset(hist_host, 0, h->C * sizeof(unsigned long long));
+    return MDC_OK;
+  }
+  const int64_t chunk = 16384;
+  return run_host_pipeline<int32_t, int32_t, int32_t>(
+      h, x_host, n, out_host, pre_host, cls_host, hist_host, chunk, ticket,
+      [h](const int32_t* x, int64_t m, int32_t* o, int32_t* p, int32_t* c, unsigned long long* hs, cudaStream_t s) {
+        return launch_q612(h, x, m, o, p, c, hs, s);
+      });
+}
+
+int mdc_predict_f32_host(mdc_handle_t h, const float* x_host, int64_t n, float* probs_host, float* dense_host,
+                         int32_t* cls_host, unsigned long long* hist_host) {
+  return predict_f32_host_impl(h, x_host, n, probs_host, dense_host, cls_host, hist_host, nullptr);
+}
+
 int mdc_predict_f32_host_async(mdc_handle_t h, const float* x_host, int64_t n, float* probs_host, float* dense_host,
                                int32_t* cls_host, unsigned long long* hist_host, int64_t* ticket) {
   MDC_REQUIRE(ticket != nullptr, MDC_ERR_INVALID, "ticket is NULL");
-  *ticket = 0;                                   // 0: nothing pending (the call below was synchronous)
-  MDC_CHECK_HANDLE(h);
-  if (h->model == MDC_MODEL_VT && h->mode != MDC_MODE_FP32 && n > 0) {
-    MDC_REQUIRE(x_host != nullptr, MDC_ERR_INVALID, "x_host is NULL");
-    if (int e = ensure_packed(h)) return e;
-    return run_vt_host_pipeline(h, x_host, n, probs_host, dense_host, cls_host, hist_host, ticket);
-  }
-  return mdc_predict_f32_host(h, x_host, n, probs_host, dense_host, cls_host, hist_host);
+  *ticket = 0;                                   // 0: nothing pending (e.g. n == 0)
+  return predict_f32_host_impl(h, x_host, n, probs_host, dense_host, cls_host, hist_host, ticket);
+}
+
+int mdc_predict_q612_host_async(mdc_handle_t h, const int32_t* x_host, int64_t n, int32_t* out_host, int32_t* pre_host,
+                                int32_t* cls_host, unsigned long long* hist_host, int64_t* ticket) {
+  MDC_REQUIRE(ticket != nullptr, MDC_ERR_INVALID, "ticket is NULL");
+  *ticket = 0;
+  return predict_q612_host_impl(h, x_host, n, out_host, pre_host, cls_host, hist_host, ticket);
 }
 
 int mdc_host_wait(mdc_handle_t h, int64_t ticket) {
@@ -528,20 +562,7 @@ int mdc_host_wait(mdc_handle_t h, int64_t ticket) {
 
 int mdc_predict_q612_host(mdc_handle_t h, const int32_t* x_host, int64_t n, int32_t* out_host, int32_t* pre_host,
                           int32_t* cls_host, unsigned long long* hist_host) {
-  MDC_CHECK_HANDLE(h);
-  MDC_REQUIRE(h->mode == MDC_MODE_Q612, MDC_ERR_INVALID, "handle is not in Q6.12 mode");
-  MDC_REQUIRE(h->have_q, MDC_ERR_NOT_READY, "ROM tables not set (call mdc_set_weights_q612)");
-  MDC_REQUIRE(n >= 0 && (n == 0 || x_host), MDC_ERR_INVALID, "bad x_host / n");
-  if (n == 0) {
-    if (hist_host) memset(hist_host, 0, h->C * sizeof(unsigned long long));
-    return MDC_OK;
-  }
-  const int64_t chunk = 16384;
-  return run_host_pipeline<int32_t, int32_t, int32_t>(
-      h, x_host, n, out_host, pre_host, cls_host, hist_host, chunk,
-      [h](const int32_t* x, int64_t m, int32_t* o, int32_t* p, int32_t* c, unsigned long long* hs, cudaStream_t s) {
-        return launch_q612(h, x, m, o, p, c, hs, s);
-      });
+  return predict_q612_host_impl(h, x_host, n, out_host, pre_host, cls_host, hist_host, nullptr);
 }
 
 // ---- FWHT ------------------------------------------------------------------------------

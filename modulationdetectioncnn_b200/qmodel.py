@@ -92,6 +92,22 @@ class FixedPointCNN2:
             raise ValueError("output must be 'out', 'pre' or 'argmax'")
         return self._run(x, [key])[key]
 
+    def predict_async(self, x, output: str = "out"):
+        """Streaming form of :meth:`predict` for host (numpy) batches, see ``CNN2Model.predict_async``."""
+        from .model import PendingPrediction
+        import ctypes as C
+        key = {"out": "out", "pre": "pre", "argmax": "cls"}.get(output)
+        if key is None:
+            raise ValueError("output must be 'out', 'pre' or 'argmax'")
+        xa = np.ascontiguousarray(x, dtype=np.int32).reshape(-1, 256)
+        n = xa.shape[0]
+        out = np.empty((n,), dtype=np.int32) if key == "cls" else np.empty((n, self.classes), dtype=np.int32)
+        ptr = lambda k: out.ctypes.data if k == key else None  # noqa: E731
+        ticket = C.c_int64(0)
+        _lib.check(self._h._lib.mdc_predict_q612_host_async(self._h.ptr, xa.ctypes.data, n, ptr("out"), ptr("pre"),
+                                                            ptr("cls"), None, C.byref(ticket)))
+        return PendingPrediction(self, ticket.value, out, xa)
+
     def class_histogram(self, x):
         return self._run(x, ["hist"])["hist"]
 

@@ -170,13 +170,27 @@ def test_predict_async_stream_matches_sync(vt, mode):
     assert np.array_equal(p1.result(), want[1].argmax(-1))
 
 
-def test_predict_async_on_unpipelined_models_is_synchronous(h5w):
+def test_predict_async_tiny_and_integer_models(h5w, qsets):
+    """The chunked host pipeline of the TinyCNN2 / integer paths streams too: several batches in flight, same results."""
+    import torch
     from modulationdetectioncnn_b200 import synth
     from modulationdetectioncnn_b200.model import tiny_cnn2
+    from modulationdetectioncnn_b200.qmodel import FixedPointCNN2
+    from modulationdetectioncnn_b200.svtext import QWeights
     m = tiny_cnn2(3, 3)
     m.set_weights(h5w["A_3conv"])
-    x = synth.iq_frames(1000)
-    assert np.array_equal(m.predict_async(x).result(), m.predict(x))
+    q = FixedPointCNN2(3, 3)
+    q.set_tables(QWeights(*[a.copy() for a in qsets["A"]]))
+    pin = lambda a: torch.from_numpy(a).pin_memory().numpy()  # noqa: E731
+    xs = [pin(synth.iq_frames(n, seed=n)) for n in (1000, 16384 * 2 + 3, 1, 40000)]
+    qs = [pin(synth.q612_frames(n, seed=n)) for n in (500, 16384 + 1, 70000)]
+    want = [m.predict(x) for x in xs]
+    wantq = [q.predict(x, output="pre") for x in qs]
+    pend = [m.predict_async(x) for x in xs]
+    pendq = [q.predict_async(x, output="pre") for x in qs]
+    for p, w in zip(pend + pendq, want + wantq):
+        assert np.array_equal(p.result(), w)
+    assert np.array_equal(q.predict_async(qs[0], output="argmax").result(), q.predict(qs[0], output="argmax"))
 
 
 def test_device_predict_is_cuda_graph_capturable(vt):
