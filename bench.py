@@ -145,7 +145,8 @@ def run_reference(args):
     m.predict(x, batch_size=256)
     rate = 256 / (time.perf_counter() - t)
     total = args.steps + args.warmup
-    n = int(min(BATCH, max(256, rate * 120.0 / total))) // 256 * 256      # whole run <= ~2 min
+    budget = float(os.environ.get("MDC_BENCH_REF_SECONDS", 120.0))        # whole run <= ~2 min
+    n = int(min(BATCH, max(256, rate * budget / total))) // 256 * 256
     x = synth.iq_frames(n, seed=2016)
     for _ in range(args.warmup):
         m.predict(x, batch_size=256)
