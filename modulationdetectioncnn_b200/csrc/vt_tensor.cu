@@ -5,15 +5,19 @@
 // Layer stack: /root/reference/examples-master/modulation_recognition/
 // RML2016.10a_VTCNN2_example.ipynb:231-243 (shapes :194-216); Dropout = identity.
 //
-// Two persistent, warp-specialised tcgen05 kernels plus the small fp32 head of vt_f32.cu:
+// Persistent, warp-specialised tcgen05 kernels:
 //
-//   vt_conv_bf16_kernel   conv1 (1x3, 256 ch, fp32 FMA on CUDA cores, produced straight into the
-//                         shared-memory A operand) -> conv2 (2x3, 80 ch) as an implicit GEMM
-//                         M = frames*132, N = 80, K = 3 taps x 512 (row,channel) -> +bias, ReLU
-//                         -> bf16 activations act[frames*132][80]   (== Keras channels_last flatten)
-//   vt_dense_bf16_kernel  act[frames][10560] x W3 -> +bias, ReLU -> h[frames][256] fp32
-//                         (TMA 128B-swizzled tiles, M = 256 per CTA, N = 256, K = 10560)
-//   vt_head_kernel        Dense(C) + softmax + argmax + histogram (fp32, vt_f32.cu)
+//   vt_conv_kernel<TF32>      conv1 (1x3, 256 ch, fp32 FMA on CUDA cores, produced straight into the
+//                             shared-memory A operand) -> conv2 (2x3, 80 ch) as an implicit GEMM
+//                             M = frames*132, N = 80, K = 3 taps x 512 (row,channel) -> +bias, ReLU
+//                             -> activations act[frames*132][80]  (== Keras channels_last flatten):
+//                             bf16, or fp32 hi / lo matrices in 3xTF32 mode
+//   vt_dense_bf16_kernel<C>   act[frames][10560] x W3 -> +bias, ReLU -> Dense(C) -> softmax, argmax,
+//                             histogram in the epilogue (TMA 128B-swizzled tiles, M = 256 per CTA,
+//                             N = 256, K = 10560); h never goes to HBM
+//   vt_dense_tf32x3_kernel    the same dense1 in 3xTF32 with fp32 master sums in registers, then
+//   vt_head_kernel            Dense(C) + softmax + argmax + histogram (fp32, vt_f32.cu)
+//   vt_conv240_kernel         experimental second bf16 conv formulation (taps as N), MDC_VT_CONV=n240
 //
 // The implicit GEMM keeps conv1's padded output positions as GEMM rows: frame f owns rows
 // [132 f, 132 f + 134) of one long activation "tape" whose rows 132 f and 132 f + 1 are the zero
