@@ -41,7 +41,10 @@ enum {
   MDC_ERR_INVALID = -1,     /* bad argument / wrong model kind or mode for this call */
   MDC_ERR_CUDA = -2,        /* CUDA runtime/driver error (text in mdc_last_error) */
   MDC_ERR_NOT_READY = -3,   /* weights not (completely) set */
-  MDC_ERR_UNSUPPORTED = -4  /* shape outside what the kernels implement */
+  MDC_ERR_UNSUPPORTED = -4, /* shape outside what the kernels implement */
+  MDC_ERR_RANGE = -5        /* MDC_MODE_F16X3 only: an input or activation left the range the fp16 hi/lo split
+                               represents (|value| > 65504); the results of the call are not to be trusted -
+                               rerun it on an MDC_MODE_TF32X3 handle (the Python facade does so by itself) */
 };
 
 /* model kinds */
@@ -56,7 +59,19 @@ enum {
   MDC_MODE_BF16 = 1,   /* VT-CNN2 only: bf16 operands, fp32 accumulate, tcgen05 tensor cores */
   MDC_MODE_TF32X3 = 2, /* VT-CNN2 only: every fp32 operand split into tf32 hi + lo, three tcgen05 kind::tf32
                           MMAs per product; fp32-level accuracy (<=1e-5 of the fp64 oracle) on tensor cores */
-  MDC_MODE_Q612 = 3    /* TinyCNN2 only: bit-exact 18-bit Q6.12 SystemVerilog datapath */
+  MDC_MODE_Q612 = 3,   /* TinyCNN2 only: bit-exact 18-bit Q6.12 SystemVerilog datapath */
+  MDC_MODE_F16X3 = 4   /* VT-CNN2 only: every fp32 operand split into fp16 hi + 2^-11 fp16 lo, three tcgen05 kind::f16
+                          MMAs per product at the full 16-bit rate; fp32-level accuracy (<=1e-5 of the fp64 oracle)
+                          at ~2x the TF32X3 rate.  Values must stay inside the fp16 range (MDC_ERR_RANGE otherwise) */
+};
+
+/* frame formats of the mdc_predict_raw* calls (VT-CNN2 tensor-core modes convert them inside the frame load) */
+enum {
+  MDC_IN_F32 = 0,  /* f32 [n,2,128], row 0 = I, row 1 = Q: what model.predict receives (cnn.py:198)            */
+  MDC_IN_U8IQ = 1, /* u8 [n,128,2]: raw RTL-SDR bytes I0 Q0 I1 Q1 ... (README.md:5); value = (u - 127.5)/128,
+                      identical to mdc_sdr_ingest_u8 followed by mdc_predict_f32.  256 B per frame               */
+  MDC_IN_I16 = 2   /* i16 [n,256]: Q6.12 samples in the test_table address map (0-127 I, 128-255 Q,
+                      cnn_test_latest1.sv:88-102), value = s / 4096.  512 B per frame                             */
 };
 
 /* tensor ids for mdc_set_weights_f32 (Keras layouts: conv (kh,kw,cin,cout), dense (in,out)) */
@@ -112,9 +127,26 @@ MDC_API int mdc_predict_f32(mdc_handle_t h, const float* x_dev, int64_t n, float
                             float* dense_dev, int32_t* cls_dev, unsigned long long* hist_dev,
                             void* stream);
 
+/* Size the handle's work space for calls of up to max_frames frames (clamped to the pass size the mode uses), and
+ * pack the weights: after it, mdc_predict_f32 / mdc_predict_raw only enqueue kernels - no allocation, copy or
+ * synchronisation - from the very first call, which is what capturing them into a CUDA graph requires.  A graph
+ * captured earlier stays valid as long as no later call or mdc_reserve asks for MORE frames (growing the work space
+ * moves it).  Weights must be set.                                                                               */
+MDC_API int mdc_reserve(mdc_handle_t h, int64_t max_frames);
+
+/* mdc_predict_f32 for frames in one of the MDC_IN_* formats.  MDC_IN_U8IQ / MDC_IN_I16 need a VT-CNN2 handle in a
+ * tensor-core mode (BF16, F16X3, TF32X3); x_dev must be 16-byte aligned.                                          */
+MDC_API int mdc_predict_raw(mdc_handle_t h, const void* x_dev, int in_format, int64_t n, float* probs_dev,
+                            float* dense_dev, int32_t* cls_dev, unsigned long long* hist_dev, void* stream);
+
+/* MDC_MODE_F16X3: *flags = bit 0 set when some call since the last reset saw an input or activation outside the
+ * fp16 range (see MDC_ERR_RANGE).  Synchronises the device.  The host-buffer calls below check it themselves.    */
+MDC_API int mdc_range_flags(mdc_handle_t h, unsigned int* flags, int reset);
+
 /* Same call with HOST buffers (what a numpy caller has): copies x in chunks on internal
  * streams, overlapping H2D / kernels / D2H, and returns when the outputs are in host memory.
- * Pinned buffers make the copies asynchronous; pageable buffers work but serialise.
+ * x_host may be ordinary pageable memory (what cnn.py:198,237 pass): the library then stages it through its own
+ * pinned ring with a few copy threads; pinned (cudaHostAlloc / cudaHostRegister'ed) input is copied directly.
  * hist_host u64[C] is overwritten (not accumulated).                                      */
 MDC_API int mdc_predict_f32_host(mdc_handle_t h, const float* x_host, int64_t n, float* probs_host,
                                  float* dense_host, int32_t* cls_host,
@@ -128,6 +160,13 @@ MDC_API int mdc_predict_f32_host_async(mdc_handle_t h, const float* x_host, int6
                                        float* dense_host, int32_t* cls_host,
                                        unsigned long long* hist_host, int64_t* ticket);
 MDC_API int mdc_host_wait(mdc_handle_t h, int64_t ticket);
+
+/* The two host-buffer calls for frames in one of the MDC_IN_* formats (a quarter / half of the bytes over PCIe).   */
+MDC_API int mdc_predict_raw_host(mdc_handle_t h, const void* x_host, int in_format, int64_t n, float* probs_host,
+                                 float* dense_host, int32_t* cls_host, unsigned long long* hist_host);
+MDC_API int mdc_predict_raw_host_async(mdc_handle_t h, const void* x_host, int in_format, int64_t n,
+                                       float* probs_host, float* dense_host, int32_t* cls_host,
+                                       unsigned long long* hist_host, int64_t* ticket);
 
 /* ---- integer (SystemVerilog-exact) inference ------------------------------------------
  * Replaces: one reset-to-done run of `layers_top` (cnn_test_latest1.sv:144-209) per frame,
@@ -197,7 +236,9 @@ MDC_API int mdc_profile_read(mdc_handle_t h, double* ms_total, int64_t* launches
  * FP32 mode, f32 hi matrix then lo matrix in TF32X3 mode) - `model3`-style layer taps of CNN.ipynb cell 17;
  * what = 1: dense1 activations f32 [frames][256] (BF16 mode fuses the rest of the network into the dense1
  * kernel and keeps no copy unless the process runs with MDC_VT_KEEP_H=1).  bytes is clamped to the workspace
- * size; returns the bytes copied in *copied. */
+ * size; returns the bytes copied in *copied.
+ * (F16X3 mode: what = 0 gives the fp16 hi matrix then the lo matrix, [frames*132][80] each, of the pass size
+ * the work space was reserved for.) */
 MDC_API int mdc_debug_read(mdc_handle_t h, int what, void* host_dst, size_t bytes, size_t* copied);
 
 #ifdef __cplusplus

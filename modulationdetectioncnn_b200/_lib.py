@@ -15,7 +15,9 @@ LIB_PATH = os.path.join(HERE, "libmdc.so")
 # enums of include/mdc.h
 MDC_OK = 0
 MODEL_TINY, MODEL_VT = 0, 1
-MODE_FP32, MODE_BF16, MODE_TF32X3, MODE_Q612 = 0, 1, 2, 3
+MODE_FP32, MODE_BF16, MODE_TF32X3, MODE_Q612, MODE_F16X3 = 0, 1, 2, 3, 4
+IN_F32, IN_U8IQ, IN_I16 = 0, 1, 2
+ERR_RANGE = -5
 T_CONV1_K, T_CONV1_B, T_CONV2_K, T_CONV2_B, T_DENSE1_K, T_DENSE1_B, T_DENSE2_K, T_DENSE2_B = range(8)
 OPT_FLATTEN_ORDER = 0
 FWHT_NATURAL, FWHT_SEQUENCY = 0, 1
@@ -25,6 +27,7 @@ EXPORTS = [
     "mdc_predict_f32", "mdc_predict_f32_host", "mdc_predict_f32_host_async", "mdc_host_wait", "mdc_predict_q612", "mdc_predict_q612_host_async", "mdc_predict_q612_host",
     "mdc_fwht_i32", "mdc_fwht_i32_host", "mdc_sdr_ingest_u8", "mdc_confusion_i32", "mdc_confusion_grouped_i32", "mdc_last_error", "mdc_version",
     "mdc_launch_count", "mdc_profile_enable", "mdc_profile_read", "mdc_debug_read",
+    "mdc_reserve", "mdc_predict_raw", "mdc_predict_raw_host", "mdc_predict_raw_host_async", "mdc_range_flags",
 ]
 
 
@@ -71,6 +74,11 @@ def load() -> C.CDLL:
         "mdc_profile_enable": (i32, [vp, i32]),
         "mdc_profile_read": (i32, [vp, C.POINTER(C.c_double), C.POINTER(i64), C.POINTER(C.c_char_p)]),
         "mdc_debug_read": (i32, [vp, i32, vp, sz, C.POINTER(sz)]),
+        "mdc_reserve": (i32, [vp, i64]),
+        "mdc_predict_raw": (i32, [vp, vp, i32, i64, vp, vp, vp, vp, vp]),
+        "mdc_predict_raw_host": (i32, [vp, vp, i32, i64, vp, vp, vp, vp]),
+        "mdc_predict_raw_host_async": (i32, [vp, vp, i32, i64, vp, vp, vp, vp, C.POINTER(i64)]),
+        "mdc_range_flags": (i32, [vp, C.POINTER(C.c_uint), i32]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -116,6 +124,14 @@ class Handle:
 
     def launch_count(self) -> int:
         return int(self._lib.mdc_launch_count(self.ptr))
+
+    def reserve(self, max_frames: int) -> None:
+        check(self._lib.mdc_reserve(self.ptr, int(max_frames)))
+
+    def range_flags(self, reset: bool = True) -> int:
+        f = C.c_uint(0)
+        check(self._lib.mdc_range_flags(self.ptr, C.byref(f), int(reset)))
+        return int(f.value)
 
     def profile_enable(self, on: bool = True) -> None:
         check(self._lib.mdc_profile_enable(self.ptr, int(on)))

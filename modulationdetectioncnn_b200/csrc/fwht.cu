@@ -17,7 +17,7 @@ namespace mdc {
 
 __device__ __forceinline__ int4 ldg_stream_i4(const int4* p) {
   int4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
+  asm volatile("ld.global.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
                : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
   return r;
 }
@@ -35,7 +35,7 @@ __device__ __forceinline__ unsigned seq_slot(unsigned j, int log2n) {
 
 template <int LOG2N, bool SEQ>
 __global__ void __launch_bounds__(256)
-fwht_warp_kernel(const int4* __restrict__ in, int4* __restrict__ out, long long n) {
+fwht_warp_kernel(const int4* in, int4* out, long long n) {
   constexpr int N = 1 << LOG2N;
   constexpr int J = N / 128;              // int4 per lane
   extern __shared__ int smem[];           // SEQ only: 8 warps x N ints
@@ -95,7 +95,7 @@ fwht_warp_kernel(const int4* __restrict__ in, int4* __restrict__ out, long long 
 }
 
 __global__ void __launch_bounds__(256)
-fwht_block_kernel(const int* __restrict__ in, int* __restrict__ out, long long n, int log2n, int seq) {
+fwht_block_kernel(const int* in, int* out, long long n, int log2n, int seq) {
   extern __shared__ int smem[];
   const int N = 1 << log2n;
   for (long long s = blockIdx.x; s < n; s += gridDim.x) {

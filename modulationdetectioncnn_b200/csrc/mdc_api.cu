@@ -2,11 +2,126 @@
 #include <string.h>
 
 #include <algorithm>
+#include <condition_variable>
 #include <mutex>
+#include <thread>
 
 #include "mdc_internal.cuh"
 
 namespace mdc {
+
+// Makes the handle's device current for the duration of an entry point and restores the caller's device afterwards
+// (a library call must not move the calling thread's later torch / CUDA allocations to another GPU).
+struct DeviceGuard {
+  int prev = -1, dev = -1;
+  cudaError_t err = cudaSuccess;
+  explicit DeviceGuard(int device) : dev(device) {
+    err = cudaGetDevice(&prev);
+    if (err == cudaSuccess && prev != dev) err = cudaSetDevice(dev);
+  }
+  ~DeviceGuard() {
+    if (prev >= 0 && prev != dev) cudaSetDevice(prev);
+  }
+};
+
+struct PinnedBuffer {
+  void* ptr = nullptr;
+  size_t bytes = 0;
+  int reserve(size_t n) {          // grow-only
+    if (n <= bytes) return MDC_OK;
+    if (ptr) {
+      MDC_CUDA(cudaFreeHost(ptr));
+      ptr = nullptr;
+      bytes = 0;
+    }
+    MDC_CUDA(cudaHostAlloc(&ptr, n, cudaHostAllocDefault));
+    bytes = n;
+    return MDC_OK;
+  }
+  void release() {
+    if (ptr) cudaFreeHost(ptr);
+    ptr = nullptr;
+    bytes = 0;
+  }
+};
+
+// A few persistent threads that copy a caller's pageable buffer into the pinned staging ring, one slice each (a single
+// core's memcpy is slower than the PCIe link it feeds).  One pool per process, started on first use.
+class CopyPool {
+ public:
+  static CopyPool& get() {
+    static CopyPool p;
+    return p;
+  }
+  void copy(void* dst, const void* src, size_t bytes) {
+    const size_t parts = bytes < ((size_t)1 << 20) ? 1 : threads_.size() + 1;
+    if (parts == 1) {
+      memcpy(dst, src, bytes);
+      return;
+    }
+    const size_t step = ((bytes / parts) + 4095) & ~(size_t)4095;
+    size_t off = step;
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      for (; off < bytes; off += step)
+        jobs_.push_back({(char*)dst + off, (const char*)src + off, std::min(step, bytes - off)});
+      pending_ += jobs_.size();
+    }
+    cv_.notify_all();
+    memcpy(dst, src, std::min(step, bytes));       // the caller's own slice
+    std::unique_lock<std::mutex> lk(mu_);
+    done_.wait(lk, [this] { return pending_ == 0; });
+  }
+
+ private:
+  struct Job {
+    char* dst;
+    const char* src;
+    size_t n;
+  };
+  CopyPool() {
+    unsigned hw = std::thread::hardware_concurrency();
+    int n = getenv("MDC_COPY_THREADS") ? atoi(getenv("MDC_COPY_THREADS")) - 1 : (int)std::min(3u, hw / 4);
+    for (int i = 0; i < n; ++i) threads_.emplace_back([this] { work(); });
+  }
+  ~CopyPool() {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      stop_ = true;
+    }
+    cv_.notify_all();
+    for (auto& t : threads_) t.join();
+  }
+  void work() {
+    std::unique_lock<std::mutex> lk(mu_);
+    for (;;) {
+      cv_.wait(lk, [this] { return stop_ || !jobs_.empty(); });
+      if (stop_) return;
+      Job j = jobs_.back();
+      jobs_.pop_back();
+      lk.unlock();
+      memcpy(j.dst, j.src, j.n);
+      lk.lock();
+      if (--pending_ == 0) done_.notify_all();
+    }
+  }
+  std::vector<std::thread> threads_;
+  std::vector<Job> jobs_;
+  std::mutex mu_;
+  std::condition_variable cv_, done_;
+  size_t pending_ = 0;
+  bool stop_ = false;
+};
+
+// true for ordinary (pageable, unregistered) host memory - what numpy hands over
+static bool is_pageable(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return true;
+  }
+  return a.type == cudaMemoryTypeUnregistered;
+}
 
 static thread_local char g_err[1024] = "";
 
@@ -63,8 +178,13 @@ struct HostPipe {
   cudaEvent_t e_ticket[kTickets] = {}, e_hist = nullptr;
   DeviceBuffer x[kSlots], o0[kSlots], o1[kSlots], o2[kSlots];
   DeviceBuffer hist;
+  PinnedBuffer pin[kSlots];      // staging for pageable caller buffers (slot k is free again once e_h2d[k] has fired)
+  PinnedBuffer pout[3];          // blocking calls: pinned staging for pageable output arrays
+  PinnedBuffer range;            // u32 [kTickets]: F16X3 range flags as read back at the end of each call
   int init() {
     if (s_h2d) return MDC_OK;
+    if (int e = range.reserve(kTickets * sizeof(unsigned int))) return e;
+    memset(range.ptr, 0, kTickets * sizeof(unsigned int));
     MDC_CUDA(cudaStreamCreateWithFlags(&s_h2d, cudaStreamNonBlocking));
     MDC_CUDA(cudaStreamCreateWithFlags(&s_comp, cudaStreamNonBlocking));
     MDC_CUDA(cudaStreamCreateWithFlags(&s_d2h, cudaStreamNonBlocking));
@@ -86,8 +206,10 @@ struct HostPipe {
     cudaStreamSynchronize(s_h2d); cudaStreamSynchronize(s_comp); cudaStreamSynchronize(s_d2h);
     for (int i = 0; i < kSlots; ++i) {
       cudaEventDestroy(e_h2d[i]); cudaEventDestroy(e_comp[i]); cudaEventDestroy(e_d2h[i]);
-      x[i].release(); o0[i].release(); o1[i].release(); o2[i].release();
+      x[i].release(); o0[i].release(); o1[i].release(); o2[i].release(); pin[i].release();
     }
+    for (auto& b : pout) b.release();
+    range.release();
     for (int i = 0; i < 2; ++i) { cudaEventDestroy(e_pass[i]); cudaEventDestroy(e_pass_d2h[i]); }
     for (int i = 0; i < kTickets; ++i) cudaEventDestroy(e_ticket[i]);
     cudaEventDestroy(e_hist);
@@ -107,6 +229,9 @@ void destroy_pipe(mdc_handle_s* h) {
 
 static int ensure_packed(mdc_handle_s* h) {
   if (h->packed) return MDC_OK;
+  // the packed images are rewritten with blocking copies on the legacy stream, which does not order against the
+  // handle's non-blocking pipeline streams or the caller's: let every earlier prediction finish with the old weights
+  MDC_CUDA(cudaDeviceSynchronize());
   const int need_tiny[] = {MDC_T_CONV1_K, MDC_T_CONV1_B, MDC_T_DENSE1_K, MDC_T_DENSE1_B};
   if (h->model == MDC_MODEL_TINY) {
     for (int t : need_tiny)
@@ -148,11 +273,26 @@ static size_t tensor_count(const mdc_handle_s* h, int id) {
   }
 }
 
-static int predict_f32_dev(mdc_handle_s* h, const float* x, int64_t n, float* probs, float* dense,
+static bool vt_tensor_mode(const mdc_handle_s* h) {
+  return h->model == MDC_MODEL_VT && h->mode != MDC_MODE_FP32;
+}
+
+static size_t frame_bytes(int in_fmt) { return in_fmt == MDC_IN_U8IQ ? 256 : (in_fmt == MDC_IN_I16 ? 512 : 1024); }
+
+static int check_format(const mdc_handle_s* h, int in_fmt) {
+  MDC_REQUIRE(in_fmt == MDC_IN_F32 || in_fmt == MDC_IN_U8IQ || in_fmt == MDC_IN_I16, MDC_ERR_INVALID,
+              "unknown frame format %d", in_fmt);
+  MDC_REQUIRE(in_fmt == MDC_IN_F32 || vt_tensor_mode(h), MDC_ERR_UNSUPPORTED,
+              "raw u8 / int16 frames are read by the VT-CNN2 tensor-core kernels only (BF16, F16X3, TF32X3); "
+              "use mdc_sdr_ingest_u8 in front of this model");
+  return MDC_OK;
+}
+
+static int predict_f32_dev(mdc_handle_s* h, const void* x, int in_fmt, int64_t n, float* probs, float* dense,
                            int32_t* cls, unsigned long long* hist, cudaStream_t stream) {
-  if (h->model == MDC_MODEL_TINY) return launch_tiny_f32(h, x, n, probs, dense, cls, hist, stream);
-  if (h->mode == MDC_MODE_FP32) return launch_vt_f32(h, x, n, probs, dense, cls, hist, stream);
-  return launch_vt_bf16(h, x, n, probs, dense, cls, hist, stream);
+  if (h->model == MDC_MODEL_TINY) return launch_tiny_f32(h, (const float*)x, n, probs, dense, cls, hist, stream);
+  if (h->mode == MDC_MODE_FP32) return launch_vt_f32(h, (const float*)x, n, probs, dense, cls, hist, stream);
+  return launch_vt_bf16(h, x, in_fmt, n, probs, dense, cls, hist, stream);
 }
 
 }  // namespace mdc
@@ -160,9 +300,72 @@ static int predict_f32_dev(mdc_handle_s* h, const float* x, int64_t n, float* pr
 using namespace mdc;
 
 // ---- host-buffer variants --------------------------------------------------------------
+// One H2D chunk.  Pinned caller memory is copied directly; pageable memory (what numpy hands over, cnn.py:198) goes
+// through pinned slot k first - cudaMemcpyAsync from pageable memory would stage it on ONE driver thread and block.
+static int h2d_chunk(HostPipe& P, int k, void* dst_dev, const void* src, size_t bytes, bool pageable) {
+  if (pageable) {
+    if (int e = P.pin[k].reserve(bytes)) return e;
+    MDC_CUDA(cudaEventSynchronize(P.e_h2d[k]));       // the previous copy out of this pinned slot has finished
+    CopyPool::get().copy(P.pin[k].ptr, src, bytes);
+    src = P.pin[k].ptr;
+  }
+  MDC_CUDA(cudaMemcpyAsync(dst_dev, src, bytes, cudaMemcpyHostToDevice, P.s_h2d));
+  MDC_CUDA(cudaEventRecord(P.e_h2d[k], P.s_h2d));
+  return MDC_OK;
+}
+
+// End of a host call: histogram (and, F16X3, the range flags) back on the compute stream - after this call's last
+// kernel, before the next call's memset - then the completion event on the D2H stream.
 // ticket == NULL: synchronous (returns with the outputs in host memory); otherwise returns after enqueueing and
-// *ticket names the completion event (mdc_host_wait).  Slot counters run on across calls, so a later call's first
-// chunks wait for the slots an earlier call's tail still uses.
+// *ticket names the completion event (mdc_host_wait).
+static int finish_host_call(mdc_handle_s* h, HostPipe& P, unsigned long long* hist, int64_t* ticket) {
+  const int64_t t = ++P.ticket_seq;
+  unsigned int* range_word = reinterpret_cast<unsigned int*>(P.range.ptr) + (t % HostPipe::kTickets);
+  if (hist)
+    MDC_CUDA(cudaMemcpyAsync(hist, P.hist.ptr, h->C * sizeof(unsigned long long), cudaMemcpyDeviceToHost, P.s_comp));
+  if (h->mode == MDC_MODE_F16X3) {
+    MDC_CUDA(cudaMemcpyAsync(range_word, h->vt_flags.ptr, sizeof(unsigned int), cudaMemcpyDeviceToHost, P.s_comp));
+    MDC_CUDA(cudaMemsetAsync(h->vt_flags.ptr, 0, sizeof(unsigned int), P.s_comp));
+  } else {
+    *range_word = 0;
+  }
+  MDC_CUDA(cudaEventRecord(P.e_hist, P.s_comp));
+  MDC_CUDA(cudaStreamWaitEvent(P.s_d2h, P.e_hist, 0));
+  MDC_CUDA(cudaEventRecord(P.e_ticket[t % HostPipe::kTickets], P.s_d2h));
+  if (ticket) {
+    *ticket = t;
+    return MDC_OK;
+  }
+  MDC_CUDA(cudaEventSynchronize(P.e_ticket[t % HostPipe::kTickets]));
+  MDC_REQUIRE(*range_word == 0, MDC_ERR_RANGE,
+              "MDC_MODE_F16X3: an input or activation left the fp16 range; rerun this batch on an MDC_MODE_TF32X3 handle");
+  return MDC_OK;
+}
+
+// Blocking calls with pageable OUTPUT arrays: a device-to-pageable cudaMemcpyAsync blocks the calling thread until the
+// stream gets there, which would stop the enqueue loop at every chunk.  The results go to pinned staging instead and
+// are copied to the caller's arrays after the final synchronisation.
+struct OutStage {
+  struct Item { void* user; void* pinned; size_t bytes; };
+  Item items[3];
+  int count = 0;
+  template <class T>
+  int redirect(HostPipe& P, T*& ptr, size_t elems) {
+    if (!ptr || !is_pageable(ptr)) return MDC_OK;
+    const size_t bytes = elems * sizeof(T);
+    if (int e = P.pout[count].reserve(bytes)) return e;
+    items[count] = {ptr, P.pout[count].ptr, bytes};
+    ptr = reinterpret_cast<T*>(P.pout[count].ptr);
+    ++count;
+    return MDC_OK;
+  }
+  void deliver() {
+    for (int i = 0; i < count; ++i) CopyPool::get().copy(items[i].user, items[i].pinned, items[i].bytes);
+  }
+};
+
+// Slot counters run on across calls, so a later call's first chunks wait for the slots an earlier call's tail
+// still uses.
 template <class In, class O0, class O1, class Launch>
 static int run_host_pipeline(mdc_handle_s* h, const In* x, int64_t n, O0* o0, O1* o1, int32_t* cls,
                              unsigned long long* hist, int64_t chunk, int64_t* ticket, Launch launch) {
@@ -171,6 +374,13 @@ static int run_host_pipeline(mdc_handle_s* h, const In* x, int64_t n, O0* o0, O1
   if (int e = P.init()) return e;
   const int C = h->C;
   constexpr int S = HostPipe::kSlots;
+  const bool pageable = is_pageable(x);
+  OutStage stage;
+  if (!ticket) {
+    if (int e = stage.redirect(P, o0, (size_t)n * C)) return e;
+    if (int e = stage.redirect(P, o1, (size_t)n * C)) return e;
+    if (int e = stage.redirect(P, cls, (size_t)n)) return e;
+  }
   if (hist) MDC_CUDA(cudaMemsetAsync(P.hist.ptr, 0, C * sizeof(unsigned long long), P.s_comp));
   for (int k = 0; k < S; ++k) {
     if (int e = P.x[k].reserve((size_t)chunk * kFrameElems * sizeof(In))) return e;
@@ -183,9 +393,7 @@ static int run_host_pipeline(mdc_handle_s* h, const In* x, int64_t n, O0* o0, O1
     const int k = (int)(i % S);
     const int64_t m = (n - s) < chunk ? (n - s) : chunk;
     MDC_CUDA(cudaStreamWaitEvent(P.s_h2d, P.e_comp[k], 0));        // (a never-recorded event does not block)
-    MDC_CUDA(cudaMemcpyAsync(P.x[k].ptr, x + s * kFrameElems, (size_t)m * kFrameElems * sizeof(In),
-                             cudaMemcpyHostToDevice, P.s_h2d));
-    MDC_CUDA(cudaEventRecord(P.e_h2d[k], P.s_h2d));
+    if (int e = h2d_chunk(P, k, P.x[k].ptr, x + s * kFrameElems, (size_t)m * kFrameElems * sizeof(In), pageable)) return e;
     MDC_CUDA(cudaStreamWaitEvent(P.s_comp, P.e_h2d[k], 0));
     MDC_CUDA(cudaStreamWaitEvent(P.s_comp, P.e_d2h[k], 0));
     if (int e = launch((const In*)P.x[k].ptr, m, o0 ? (O0*)P.o0[k].ptr : nullptr,
@@ -199,47 +407,46 @@ static int run_host_pipeline(mdc_handle_s* h, const In* x, int64_t n, O0* o0, O1
     if (cls) MDC_CUDA(cudaMemcpyAsync(cls + s, P.o2[k].ptr, (size_t)m * sizeof(int32_t), cudaMemcpyDeviceToHost, P.s_d2h));
     MDC_CUDA(cudaEventRecord(P.e_d2h[k], P.s_d2h));
   }
-  if (hist) {
-    // on the compute stream: after this call's last kernel, before the next call's memset
-    MDC_CUDA(cudaMemcpyAsync(hist, P.hist.ptr, C * sizeof(unsigned long long), cudaMemcpyDeviceToHost, P.s_comp));
-    MDC_CUDA(cudaEventRecord(P.e_hist, P.s_comp));
-    MDC_CUDA(cudaStreamWaitEvent(P.s_d2h, P.e_hist, 0));
-  }
-  const int64_t t = ++P.ticket_seq;
-  MDC_CUDA(cudaEventRecord(P.e_ticket[t % HostPipe::kTickets], P.s_d2h));
-  if (ticket) {
-    *ticket = t;
-    return MDC_OK;
-  }
-  MDC_CUDA(cudaEventSynchronize(P.e_ticket[t % HostPipe::kTickets]));
-  return MDC_OK;
+  const int rc = finish_host_call(h, P, hist, ticket);
+  if (rc == MDC_OK || rc == MDC_ERR_RANGE) stage.deliver();
+  return rc;
 }
 
 
-// Tensor-core VT-CNN2 (bf16 / 3xTF32) from host buffers.  The frames travel in small chunks (8 MiB) so the
-// first convolution starts early and every later copy hides under the previous chunk's convolution; dense1
-// and the head run ONCE per pass over all the activations (a dense tile is 256 frames per SM: per-chunk
-// launches would leave most SMs idle), and the pass's results are copied back under the next pass.
-// ticket == NULL: synchronous (returns with the outputs in host memory); otherwise returns after enqueueing and
-// *ticket names the completion event (mdc_host_wait)
-static int run_vt_host_pipeline(mdc_handle_s* h, const float* x, int64_t n, float* probs, float* dense, int32_t* cls,
-                                unsigned long long* hist, int64_t* ticket) {
+// Tensor-core VT-CNN2 (bf16 / fp16x3 / 3xTF32) from host buffers, frames in any MDC_IN_* format.  The frames travel in
+// small chunks (8 MiB of f32) so the first convolution starts early and every later copy hides under the previous
+// chunk's convolution; dense1 and the head run ONCE per pass over all the activations (a dense tile is 128 / 256
+// frames per SM: per-chunk launches would leave most SMs idle), and the pass's results are copied back under the
+// next pass.
+static int run_vt_host_pipeline(mdc_handle_s* h, const void* xv, int in_fmt, int64_t n, float* probs, float* dense,
+                                int32_t* cls, unsigned long long* hist, int64_t* ticket) {
   if (!h->pipe) h->pipe = new HostPipe();
   HostPipe& P = *h->pipe;
   if (int e = P.init()) return e;
   const int C = h->C;
   constexpr int S = HostPipe::kSlots;
+  const uint8_t* x = reinterpret_cast<const uint8_t*>(xv);
+  const size_t fb = frame_bytes(in_fmt);
+  const bool pageable = is_pageable(xv);
+  OutStage stage;
+  if (!ticket) {
+    if (int e = stage.redirect(P, probs, (size_t)n * C)) return e;
+    if (int e = stage.redirect(P, dense, (size_t)n * C)) return e;
+    if (int e = stage.redirect(P, cls, (size_t)n)) return e;
+  }
   // bf16, blocking call: passes of 32,768 frames (128 dense tiles, one wave) so that dense1 of the first half runs
   // under the second half's copies and convolutions, 8 MiB chunks after a 2 MiB first one (nothing overlaps the very
   // first copy).  Streaming call: the tail of this call runs under the next call's copies anyway, so one dense1
   // launch per 65,536 frames and 16 MiB chunks (fewer ~30 us launch prologues) win: measured per 65,536 frames,
   // blocking / streaming: 1.92 / 1.74 ms with the first setting, 2.04 / 1.70 ms with the second.
+  // fp16x3: the kernels take three times as long as the copies, one 65,536-frame pass either way.
   // (MDC_VT_PASS / MDC_VT_CHUNK / MDC_VT_FIRST: tuning aids, override both)
   const bool streaming = ticket != nullptr;
   static const int64_t ov_pass = getenv("MDC_VT_PASS") ? atoll(getenv("MDC_VT_PASS")) : 0;
   static const int64_t ov_chunk = getenv("MDC_VT_CHUNK") ? atoll(getenv("MDC_VT_CHUNK")) : 0;
   static const int64_t ov_first = getenv("MDC_VT_FIRST") ? atoll(getenv("MDC_VT_FIRST")) : 0;
-  const int64_t env_pass = ov_pass ? ov_pass : (streaming ? 65536 : 32768);
+  const bool one_pass = streaming || h->mode == MDC_MODE_F16X3;
+  const int64_t env_pass = ov_pass ? ov_pass : (one_pass ? 65536 : 32768);
   const int64_t env_chunk = ov_chunk ? ov_chunk : (streaming ? 16384 : 8192);
   const int64_t env_first = ov_first ? ov_first : (streaming ? 16384 : 2048);
   const bool tf32 = h->mode == MDC_MODE_TF32X3;
@@ -249,7 +456,7 @@ static int run_vt_host_pipeline(mdc_handle_s* h, const float* x, int64_t n, floa
   if (int e = vt_reserve(h, cap)) return e;
   if (hist) MDC_CUDA(cudaMemsetAsync(P.hist.ptr, 0, C * sizeof(unsigned long long), P.s_comp));
   for (int k = 0; k < S; ++k)
-    if (int e = P.x[k].reserve((size_t)(cap < chunk ? cap : chunk) * kFrameElems * sizeof(float))) return e;
+    if (int e = P.x[k].reserve((size_t)(cap < chunk ? cap : chunk) * fb)) return e;
   for (int b = 0; b < 2; ++b) {
     if (probs) if (int e = P.o0[b].reserve((size_t)cap * C * sizeof(float))) return e;
     if (dense) if (int e = P.o1[b].reserve((size_t)cap * C * sizeof(float))) return e;
@@ -266,11 +473,9 @@ static int run_vt_host_pipeline(mdc_handle_s* h, const float* x, int64_t n, floa
       step = (p0 == 0 && c0 == 0 && !tf32 && pm > 2 * env_first) ? env_first : chunk;
       const int64_t m = (pm - c0) < step ? (pm - c0) : step;
       MDC_CUDA(cudaStreamWaitEvent(P.s_h2d, P.e_comp[k], 0));     // (a never-recorded event does not block)
-      MDC_CUDA(cudaMemcpyAsync(P.x[k].ptr, x + (p0 + c0) * kFrameElems, (size_t)m * kFrameElems * sizeof(float),
-                               cudaMemcpyHostToDevice, P.s_h2d));
-      MDC_CUDA(cudaEventRecord(P.e_h2d[k], P.s_h2d));
+      if (int e = h2d_chunk(P, k, P.x[k].ptr, x + (size_t)(p0 + c0) * fb, (size_t)m * fb, pageable)) return e;
       MDC_CUDA(cudaStreamWaitEvent(P.s_comp, P.e_h2d[k], 0));
-      if (int e = launch_vt_conv(h, (const float*)P.x[k].ptr, m, c0, P.s_comp)) return e;
+      if (int e = launch_vt_conv(h, P.x[k].ptr, in_fmt, m, c0, P.s_comp)) return e;
       MDC_CUDA(cudaEventRecord(P.e_comp[k], P.s_comp));
     }
     MDC_CUDA(cudaStreamWaitEvent(P.s_comp, P.e_pass_d2h[ob], 0));
@@ -285,20 +490,9 @@ static int run_vt_host_pipeline(mdc_handle_s* h, const float* x, int64_t n, floa
     if (cls) MDC_CUDA(cudaMemcpyAsync(cls + p0, P.o2[ob].ptr, (size_t)pm * sizeof(int32_t), cudaMemcpyDeviceToHost, P.s_d2h));
     MDC_CUDA(cudaEventRecord(P.e_pass_d2h[ob], P.s_d2h));
   }
-  if (hist) {
-    // on the compute stream: after this call's last dense1 launch, before the next call's memset
-    MDC_CUDA(cudaMemcpyAsync(hist, P.hist.ptr, C * sizeof(unsigned long long), cudaMemcpyDeviceToHost, P.s_comp));
-    MDC_CUDA(cudaEventRecord(P.e_hist, P.s_comp));
-    MDC_CUDA(cudaStreamWaitEvent(P.s_d2h, P.e_hist, 0));
-  }
-  const int64_t t = ++P.ticket_seq;
-  MDC_CUDA(cudaEventRecord(P.e_ticket[t % HostPipe::kTickets], P.s_d2h));
-  if (ticket) {
-    *ticket = t;
-    return MDC_OK;
-  }
-  MDC_CUDA(cudaEventSynchronize(P.e_ticket[t % HostPipe::kTickets]));
-  return MDC_OK;
+  const int rc = finish_host_call(h, P, hist, ticket);
+  if (rc == MDC_OK || rc == MDC_ERR_RANGE) stage.deliver();
+  return rc;
 }
 
 // ---- confusion matrix (optionally one per group, e.g. per SNR) -----------------------------
@@ -329,12 +523,13 @@ __global__ void confusion_kernel(const int* __restrict__ t, const int* __restric
 
 #define MDC_CHECK_HANDLE(h)                                                   \
   MDC_REQUIRE((h) != nullptr, MDC_ERR_INVALID, "null handle");                \
-  MDC_CUDA(cudaSetDevice((h)->device))
+  mdc::DeviceGuard mdc_device_guard_((h)->device);                            \
+  MDC_CUDA(mdc_device_guard_.err)
 
 extern "C" {
 
 const char* mdc_last_error(void) { return g_err; }
-const char* mdc_version(void) { return "libmdc 0.1.0 (sm_100a)"; }
+const char* mdc_version(void) { return "libmdc 0.2.0 (sm_100a)"; }
 
 int mdc_create(int model_kind, int filters, int classes, int mode, int device, mdc_handle_t* out) {
   MDC_REQUIRE(out != nullptr, MDC_ERR_INVALID, "out is NULL");
@@ -349,13 +544,15 @@ int mdc_create(int model_kind, int filters, int classes, int mode, int device, m
     MDC_REQUIRE(mode == MDC_MODE_FP32 || mode == MDC_MODE_Q612, MDC_ERR_INVALID,
                 "TinyCNN2 supports MDC_MODE_FP32 and MDC_MODE_Q612, not mode %d", mode);
   } else {
-    MDC_REQUIRE(mode == MDC_MODE_FP32 || mode == MDC_MODE_BF16 || mode == MDC_MODE_TF32X3, MDC_ERR_INVALID,
-                "VT-CNN2 supports MDC_MODE_FP32, MDC_MODE_BF16 and MDC_MODE_TF32X3, not mode %d", mode);
+    MDC_REQUIRE(mode == MDC_MODE_FP32 || mode == MDC_MODE_BF16 || mode == MDC_MODE_TF32X3 || mode == MDC_MODE_F16X3,
+                MDC_ERR_INVALID,
+                "VT-CNN2 supports MDC_MODE_FP32, MDC_MODE_BF16, MDC_MODE_F16X3 and MDC_MODE_TF32X3, not mode %d", mode);
   }
   int ndev = 0;
   MDC_CUDA(cudaGetDeviceCount(&ndev));
   MDC_REQUIRE(device >= 0 && device < ndev, MDC_ERR_INVALID, "device %d not in [0,%d)", device, ndev);
-  MDC_CUDA(cudaSetDevice(device));
+  DeviceGuard guard(device);
+  MDC_CUDA(guard.err);
   cudaDeviceProp prop;
   MDC_CUDA(cudaGetDeviceProperties(&prop, device));
   MDC_REQUIRE(prop.major == 10, MDC_ERR_UNSUPPORTED,
@@ -370,20 +567,21 @@ int mdc_create(int model_kind, int filters, int classes, int mode, int device, m
   h->dominant_kernel = model_kind == MDC_MODEL_TINY
                            ? (mode == MDC_MODE_Q612 ? "q612_kernel" : "tiny_f32_kernel")
                            : (mode == MDC_MODE_FP32 ? "sgemm_bias_act_kernel(conv2)"
-                                                   : (mode == MDC_MODE_BF16 ? "vt_conv_kernel<bf16>" : "vt_conv_kernel<tf32x3>"));
+                                                   : (mode == MDC_MODE_BF16 ? "vt_conv_kernel<bf16>"
+                                                      : (mode == MDC_MODE_F16X3 ? "vt_conv_kernel<f16x3>" : "vt_conv_kernel<tf32x3>")));
   *out = h;
   return MDC_OK;
 }
 
 int mdc_destroy(mdc_handle_t h) {
   if (!h) return MDC_OK;
-  cudaSetDevice(h->device);
+  DeviceGuard guard(h->device);
   cudaDeviceSynchronize();
   destroy_pipe(h);
   for (auto& pr : h->prof.pending) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
   DeviceBuffer* bufs[] = {&h->tiny_conv, &h->tiny_dense, &h->tiny_bias, &h->vt_w1, &h->vt_b1, &h->vt_w2,
                           &h->vt_b2, &h->vt_w3, &h->vt_b3, &h->vt_w4, &h->vt_b4, &h->vt_w2_bf16,
-                          &h->vt_w3_bf16, &h->vt_w2_n240, &h->ws_a1, &h->ws_act, &h->ws_h, &h->q_dense};
+                          &h->vt_w3_bf16, &h->vt_flags, &h->ws_a1, &h->ws_act, &h->ws_h, &h->q_dense};
   for (DeviceBuffer* b : bufs) b->release();
   free(h->tmap_w3);
   delete h;
@@ -470,15 +668,45 @@ int mdc_set_weights_q612(mdc_handle_t h, const int32_t* conv_tab, const int32_t*
   return MDC_OK;
 }
 
-int mdc_predict_f32(mdc_handle_t h, const float* x_dev, int64_t n, float* probs_dev, float* dense_dev,
+int mdc_predict_raw(mdc_handle_t h, const void* x_dev, int in_format, int64_t n, float* probs_dev, float* dense_dev,
                     int32_t* cls_dev, unsigned long long* hist_dev, void* stream) {
   MDC_CHECK_HANDLE(h);
   MDC_REQUIRE(h->mode != MDC_MODE_Q612, MDC_ERR_INVALID, "Q6.12 handle: use mdc_predict_q612");
   MDC_REQUIRE(n >= 0, MDC_ERR_INVALID, "n=%lld < 0", (long long)n);
   MDC_REQUIRE(n == 0 || x_dev != nullptr, MDC_ERR_INVALID, "x_dev is NULL");
   MDC_REQUIRE(((uintptr_t)x_dev & 15) == 0, MDC_ERR_INVALID, "x_dev must be 16-byte aligned");
+  if (int e = check_format(h, in_format)) return e;
   if (int e = ensure_packed(h)) return e;
-  return predict_f32_dev(h, x_dev, n, probs_dev, dense_dev, cls_dev, hist_dev, (cudaStream_t)stream);
+  return predict_f32_dev(h, x_dev, in_format, n, probs_dev, dense_dev, cls_dev, hist_dev, (cudaStream_t)stream);
+}
+
+int mdc_predict_f32(mdc_handle_t h, const float* x_dev, int64_t n, float* probs_dev, float* dense_dev,
+                    int32_t* cls_dev, unsigned long long* hist_dev, void* stream) {
+  return mdc_predict_raw(h, x_dev, MDC_IN_F32, n, probs_dev, dense_dev, cls_dev, hist_dev, stream);
+}
+
+int mdc_reserve(mdc_handle_t h, int64_t max_frames) {
+  MDC_CHECK_HANDLE(h);
+  MDC_REQUIRE(max_frames >= 0, MDC_ERR_INVALID, "max_frames=%lld < 0", (long long)max_frames);
+  if (h->mode == MDC_MODE_Q612) return MDC_OK;            // the integer kernel needs no work space
+  if (int e = ensure_packed(h)) return e;
+  if (vt_tensor_mode(h)) {
+    const int64_t pass = vt_pass_frames(h);
+    MDC_CUDA(cudaDeviceSynchronize());                    // growing the work space frees the old one
+    return vt_reserve(h, max_frames < pass ? max_frames : pass);
+  }
+  return MDC_OK;
+}
+
+int mdc_range_flags(mdc_handle_t h, unsigned int* flags, int reset) {
+  MDC_CHECK_HANDLE(h);
+  MDC_REQUIRE(flags != nullptr, MDC_ERR_INVALID, "flags is NULL");
+  *flags = 0;
+  if (h->mode != MDC_MODE_F16X3 || !h->vt_flags.ptr) return MDC_OK;
+  MDC_CUDA(cudaDeviceSynchronize());
+  MDC_CUDA(cudaMemcpy(flags, h->vt_flags.ptr, sizeof(unsigned int), cudaMemcpyDeviceToHost));
+  if (reset) MDC_CUDA(cudaMemset(h->vt_flags.ptr, 0, sizeof(unsigned int)));
+  return MDC_OK;
 }
 
 int mdc_predict_q612(mdc_handle_t h, const int32_t* x_dev, int64_t n, int32_t* out_dev, int32_t* pre_dev,
@@ -492,23 +720,24 @@ int mdc_predict_q612(mdc_handle_t h, const int32_t* x_dev, int64_t n, int32_t* o
   return launch_q612(h, x_dev, n, out_dev, pre_dev, cls_dev, hist_dev, (cudaStream_t)stream);
 }
 
-static int predict_f32_host_impl(mdc_handle_t h, const float* x_host, int64_t n, float* probs_host, float* dense_host,
-                                 int32_t* cls_host, unsigned long long* hist_host, int64_t* ticket) {
+static int predict_f32_host_impl(mdc_handle_t h, const void* x_host, int in_fmt, int64_t n, float* probs_host,
+                                 float* dense_host, int32_t* cls_host, unsigned long long* hist_host, int64_t* ticket) {
   MDC_CHECK_HANDLE(h);
   MDC_REQUIRE(h->mode != MDC_MODE_Q612, MDC_ERR_INVALID, "Q6.12 handle: use mdc_predict_q612_host");
   MDC_REQUIRE(n >= 0 && (n == 0 || x_host), MDC_ERR_INVALID, "bad x_host / n");
+  if (int e = check_format(h, in_fmt)) return e;
   if (int e = ensure_packed(h)) return e;
   if (n == 0) {
     if (hist_host) memset(hist_host, 0, h->C * sizeof(unsigned long long));
     return MDC_OK;
   }
-  if (h->model == MDC_MODEL_VT && h->mode != MDC_MODE_FP32)
-    return run_vt_host_pipeline(h, x_host, n, probs_host, dense_host, cls_host, hist_host, ticket);
+  if (vt_tensor_mode(h))
+    return run_vt_host_pipeline(h, x_host, in_fmt, n, probs_host, dense_host, cls_host, hist_host, ticket);
   const int64_t chunk = 16384;
   return run_host_pipeline<float, float, float>(
-      h, x_host, n, probs_host, dense_host, cls_host, hist_host, chunk, ticket,
+      h, (const float*)x_host, n, probs_host, dense_host, cls_host, hist_host, chunk, ticket,
       [h](const float* x, int64_t m, float* p, float* d, int32_t* c, unsigned long long* hs, cudaStream_t s) {
-        return predict_f32_dev(h, x, m, p, d, c, hs, s);
+        return predict_f32_dev(h, x, MDC_IN_F32, m, p, d, c, hs, s);
       });
 }
 
@@ -532,14 +761,26 @@ static int predict_q612_host_impl(mdc_handle_t h, const int32_t* x_host, int64_t
 
 int mdc_predict_f32_host(mdc_handle_t h, const float* x_host, int64_t n, float* probs_host, float* dense_host,
                          int32_t* cls_host, unsigned long long* hist_host) {
-  return predict_f32_host_impl(h, x_host, n, probs_host, dense_host, cls_host, hist_host, nullptr);
+  return predict_f32_host_impl(h, x_host, MDC_IN_F32, n, probs_host, dense_host, cls_host, hist_host, nullptr);
+}
+
+int mdc_predict_raw_host(mdc_handle_t h, const void* x_host, int in_format, int64_t n, float* probs_host,
+                         float* dense_host, int32_t* cls_host, unsigned long long* hist_host) {
+  return predict_f32_host_impl(h, x_host, in_format, n, probs_host, dense_host, cls_host, hist_host, nullptr);
 }
 
 int mdc_predict_f32_host_async(mdc_handle_t h, const float* x_host, int64_t n, float* probs_host, float* dense_host,
                                int32_t* cls_host, unsigned long long* hist_host, int64_t* ticket) {
   MDC_REQUIRE(ticket != nullptr, MDC_ERR_INVALID, "ticket is NULL");
   *ticket = 0;                                   // 0: nothing pending (e.g. n == 0)
-  return predict_f32_host_impl(h, x_host, n, probs_host, dense_host, cls_host, hist_host, ticket);
+  return predict_f32_host_impl(h, x_host, MDC_IN_F32, n, probs_host, dense_host, cls_host, hist_host, ticket);
+}
+
+int mdc_predict_raw_host_async(mdc_handle_t h, const void* x_host, int in_format, int64_t n, float* probs_host,
+                               float* dense_host, int32_t* cls_host, unsigned long long* hist_host, int64_t* ticket) {
+  MDC_REQUIRE(ticket != nullptr, MDC_ERR_INVALID, "ticket is NULL");
+  *ticket = 0;
+  return predict_f32_host_impl(h, x_host, in_format, n, probs_host, dense_host, cls_host, hist_host, ticket);
 }
 
 int mdc_predict_q612_host_async(mdc_handle_t h, const int32_t* x_host, int64_t n, int32_t* out_host, int32_t* pre_host,
@@ -557,6 +798,8 @@ int mdc_host_wait(mdc_handle_t h, int64_t ticket) {
   // completion events fire in issue order; a ticket whose event slot has been reused is covered by the newest one
   const int64_t t = (P.ticket_seq - ticket >= HostPipe::kTickets) ? P.ticket_seq : ticket;
   MDC_CUDA(cudaEventSynchronize(P.e_ticket[t % HostPipe::kTickets]));
+  MDC_REQUIRE(reinterpret_cast<unsigned int*>(P.range.ptr)[t % HostPipe::kTickets] == 0, MDC_ERR_RANGE,
+              "MDC_MODE_F16X3: an input or activation left the fp16 range; rerun this batch on an MDC_MODE_TF32X3 handle");
   return MDC_OK;
 }
 
@@ -573,6 +816,14 @@ int mdc_fwht_i32(const int32_t* in_dev, int32_t* out_dev, int64_t n_spectra, int
   MDC_REQUIRE(n_spectra >= 0, MDC_ERR_INVALID, "n_spectra < 0");
   MDC_REQUIRE(n_spectra == 0 || (in_dev && out_dev), MDC_ERR_INVALID, "null buffer");
   MDC_REQUIRE((((uintptr_t)in_dev | (uintptr_t)out_dev) & 15) == 0, MDC_ERR_INVALID, "buffers must be 16-byte aligned");
+  {
+    // in place (in == out) is fine: a spectrum is read completely by the warp / block that then writes it.  Any
+    // other overlap would let one spectrum's stores land in another's unread input.
+    const uintptr_t a = (uintptr_t)in_dev, b = (uintptr_t)out_dev;
+    const uintptr_t bytes = (uintptr_t)n_spectra << (log2_npt + 2);
+    MDC_REQUIRE(a == b || a + bytes <= b || b + bytes <= a, MDC_ERR_INVALID,
+                "in_dev and out_dev overlap partially (identical or disjoint buffers only)");
+  }
   return launch_fwht(in_dev, out_dev, n_spectra, log2_npt, ordering, (cudaStream_t)stream);
 }
 
@@ -597,7 +848,8 @@ int mdc_fwht_i32_host(const int32_t* in_host, int32_t* out_host, int64_t n_spect
   MDC_REQUIRE(n_spectra >= 0 && (n_spectra == 0 || (in_host && out_host)), MDC_ERR_INVALID, "bad buffers");
   MDC_REQUIRE(device >= 0 && device < 16, MDC_ERR_INVALID, "device %d", device);
   if (n_spectra == 0) return MDC_OK;
-  MDC_CUDA(cudaSetDevice(device));
+  DeviceGuard guard(device);
+  MDC_CUDA(guard.err);
   std::lock_guard<std::mutex> lock(g_fwht_mu);
   FwhtPipe& P = g_fwht_pipe[device];
   constexpr int S = FwhtPipe::S;

@@ -80,8 +80,10 @@ struct mdc_handle_s {
   // VT fp32 path
   mdc::DeviceBuffer vt_w1, vt_b1, vt_w2, vt_b2, vt_w3, vt_b3, vt_w4, vt_b4;
   // VT bf16 path (packed operand images)
-  mdc::DeviceBuffer vt_w2_bf16, vt_w3_bf16, vt_w2_n240;
+  mdc::DeviceBuffer vt_w2_bf16, vt_w3_bf16;   // conv2 / dense1 operand images of the handle's tensor-core mode
   std::vector<float> vt_w1_img;  // conv1 weights as the conv kernel's by-value parameter (4 KB)
+  float vt_xlimit = 3.0e38f;     // F16X3: largest |x| for which no conv1 activation can leave the fp16 range
+  mdc::DeviceBuffer vt_flags;    // F16X3: u32 range flags the kernels OR into
   void* tmap_w3 = nullptr;      // CUtensorMap (host copy, 128 B)
   // work space
   mdc::DeviceBuffer ws_a1;      // padded conv1 activations (fp32 path)
@@ -108,13 +110,14 @@ int launch_tiny_f32(mdc_handle_s* h, const float* x, int64_t n, float* probs, fl
                     int32_t* cls, unsigned long long* hist, cudaStream_t stream);
 int launch_vt_f32(mdc_handle_s* h, const float* x, int64_t n, float* probs, float* dense,
                   int32_t* cls, unsigned long long* hist, cudaStream_t stream);
-int launch_vt_bf16(mdc_handle_s* h, const float* x, int64_t n, float* probs, float* dense,
+// the tensor-core VT-CNN2 modes; x holds frames in format in_fmt (MDC_IN_*)
+int launch_vt_bf16(mdc_handle_s* h, const void* x, int in_fmt, int64_t n, float* probs, float* dense,
                    int32_t* cls, unsigned long long* hist, cudaStream_t stream);
 // tensor-core VT-CNN2 path in two stages (the host pipeline copies and convolves chunk by chunk, then runs
 // dense1 + head once per pass)
 int64_t vt_pass_frames(const mdc_handle_s* h);
 int vt_reserve(mdc_handle_s* h, int64_t frames);
-int launch_vt_conv(mdc_handle_s* h, const float* x, int64_t m, int64_t frame_offset, cudaStream_t stream);
+int launch_vt_conv(mdc_handle_s* h, const void* x, int in_fmt, int64_t m, int64_t frame_offset, cudaStream_t stream);
 int launch_vt_dense_head(mdc_handle_s* h, int64_t m, float* probs, float* dense, int32_t* cls,
                          unsigned long long* hist, cudaStream_t stream);
 int pack_tiny(mdc_handle_s* h);

@@ -262,14 +262,20 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// the same with fp16 A/B (format code 0)
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
 // kind::tf32: fp32 words in shared memory, the tensor core reads the top 19 bits (truncation);
 // A/B format code 2, K = 8 per instruction
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-// D[tmem] (+)= A[smem] * B[smem]^T, issued by ONE thread for the CTA (SASS: UTCHMMA)
-__device__ __forceinline__ void mma_bf16_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+// D[tmem] (+)= A[smem] * B[smem]^T, issued by ONE thread for the CTA (SASS: UTCHMMA).  kind::f16 covers bf16 and
+// fp16 operands (the instruction descriptor says which)
+__device__ __forceinline__ void mma_f16_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                             uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -296,7 +302,7 @@ __device__ __forceinline__ void mma_commit_multicast(uint64_t* bar, uint16_t cta
 
 // CTA-pair MMA (M = 256: rows 0..127 from this CTA's A, 128..255 from the peer's; each CTA's
 // shared memory provides N/2 rows of B at the same offsets), issued by the leader CTA only
-__device__ __forceinline__ void mma_bf16_ss_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+__device__ __forceinline__ void mma_f16_ss_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                                  uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -352,6 +358,22 @@ __device__ __forceinline__ uint32_t cvt_bf16x2(float hi, float lo) {
   uint32_t d;
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
   return d;
+}
+
+// {hi, lo} -> f16x2, round to nearest, finite saturation (an out-of-range value becomes +-65504, never inf)
+__device__ __forceinline__ uint32_t cvt_f16x2_sat(float hi, float lo) {
+  uint32_t d;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+// f16x2 -> {lo half, hi half} as fp32 (exact)
+__device__ __forceinline__ void unpack_f16x2(uint32_t v, float& lo, float& hi) {
+  asm("{\n\t.reg .b16 l, h;\n\t"
+      "mov.b32 {l, h}, %2;\n\t"
+      "cvt.f32.f16 %0, l;\n\t"
+      "cvt.f32.f16 %1, h;\n\t}"
+      : "=f"(lo), "=f"(hi)
+      : "r"(v));
 }
 
 }  // namespace sm100

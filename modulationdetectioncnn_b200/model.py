@@ -30,11 +30,41 @@ from .h5lite import H5File
 
 __all__ = ["CNN2Model", "PendingPrediction", "tiny_cnn2", "vt_cnn2", "load_model", "read_keras_weights"]
 
-_MODES = {"fp32": _lib.MODE_FP32, "bf16": _lib.MODE_BF16, "tf32x3": _lib.MODE_TF32X3}
+_MODES = {"fp32": _lib.MODE_FP32, "bf16": _lib.MODE_BF16, "tf32x3": _lib.MODE_TF32X3, "f16x3": _lib.MODE_F16X3}
 
 
 def _is_torch(x) -> bool:
     return type(x).__module__.split(".")[0] == "torch"
+
+
+def default_device() -> int:
+    """The CUDA ordinal a model lands on when none is given: torch's current device if torch has initialised CUDA,
+    else LOCAL_RANK (torchrun: one rank per GPU), else 0."""
+    import os
+    import sys
+    torch = sys.modules.get("torch")
+    if torch is not None and torch.cuda.is_available() and torch.cuda.is_initialized():
+        return int(torch.cuda.current_device())
+    return int(os.environ.get("LOCAL_RANK", 0))
+
+
+def pinned_empty(shape, dtype) -> np.ndarray:
+    """Page-locked host array (device-to-host copies into it are truly asynchronous); the array keeps its torch
+    storage alive."""
+    import torch
+    t = torch.empty(tuple(shape), dtype=getattr(torch, np.dtype(dtype).name), pin_memory=True)
+    return t.numpy()
+
+
+def _frames_of(x):
+    """(array [N, row bytes], MDC_IN_* format) for a host batch: float -> f32 [N,2,128]; uint8 -> raw interleaved
+    I/Q bytes [N,128,2]; int16 -> Q6.12 samples [N,2,128] (the test_table address map)."""
+    a = np.asarray(x)
+    if a.dtype == np.uint8:
+        return np.ascontiguousarray(a).reshape(-1, 256), _lib.IN_U8IQ
+    if a.dtype == np.int16:
+        return np.ascontiguousarray(a).reshape(-1, 256), _lib.IN_I16
+    return np.ascontiguousarray(a, dtype=np.float32).reshape(-1, 256), _lib.IN_F32
 
 
 def read_keras_weights(filepath: str) -> List[np.ndarray]:
@@ -63,15 +93,20 @@ class CNN2Model:
     """TinyCNN2(F,C) or VT-CNN2(C) behind ``load_weights / predict / evaluate``."""
 
     def __init__(self, kind: str, filters: int = 3, classes: int = 3, mode: str = "fp32",
-                 device: int = 0, flatten: str = "channels_last"):
+                 device: Optional[int] = None, flatten: str = "channels_last"):
         if kind not in ("tiny", "vt"):
             raise ValueError("kind must be 'tiny' or 'vt'")
         if mode not in _MODES:
             raise ValueError(f"mode must be one of {sorted(_MODES)}")
         if kind == "tiny" and mode != "fp32":
             raise ValueError("TinyCNN2 float inference is fp32 (integer mode: FixedPointCNN2)")
+        device = default_device() if device is None else int(device)
         self.kind, self.filters, self.classes, self.mode, self.device = kind, filters, classes, mode, device
         self.flatten = flatten
+        # f16x3: verify after every call that no value left the fp16 range and recompute in tf32x3 if one did
+        # (the check synchronises; set False to keep CUDA-tensor calls asynchronous and poll range_ok() yourself)
+        self.check_range = True
+        self._fallback: Optional["CNN2Model"] = None
         self._weights: List[np.ndarray] = []
         self._h = _lib.Handle(_lib.MODEL_TINY if kind == "tiny" else _lib.MODEL_VT, filters, classes,
                               _MODES[mode], device)
@@ -103,6 +138,8 @@ class CNN2Model:
             _lib.check(self._h._lib.mdc_set_weights_f32(self._h.ptr, tid, a.ctypes.data, a.size))
             ws.append(a)
         self._weights = ws
+        if self._fallback is not None:
+            self._fallback.set_weights(ws)
 
     def get_weights(self) -> List[np.ndarray]:
         return [w.copy() for w in self._weights]
@@ -111,13 +148,35 @@ class CNN2Model:
         self.set_weights(read_keras_weights(filepath))
 
     # ------------------------------------------------------------------ inference
+    def _tf32_twin(self) -> "CNN2Model":
+        """f16x3 only: the handle that reruns a batch whose values left the fp16 range (MDC_ERR_RANGE)."""
+        if self._fallback is None:
+            self._fallback = CNN2Model("vt", 0, self.classes, "tf32x3", self.device, self.flatten)
+            self._fallback.set_weights(self._weights)
+        return self._fallback
+
+    def range_ok(self) -> bool:
+        """f16x3: True if no call since the last check saw a value outside the fp16 range (synchronises)."""
+        return self._h.range_flags(reset=True) == 0
+
+    def reserve(self, max_frames: int) -> None:
+        """Size the work space (and pack the weights) so that later calls only enqueue kernels (mdc_reserve)."""
+        self._h.reserve(max_frames)
+
     def _run(self, x, want_probs: bool, want_dense: bool, want_cls: bool, want_hist: bool) -> Dict[str, object]:
         lib, Cn = self._h._lib, self.classes
         if _is_torch(x):
             import torch
             if not x.is_cuda:
                 raise ValueError("torch inputs must be CUDA tensors (pass numpy for the host path)")
-            xt = x.reshape(-1, 256).to(torch.float32).contiguous()
+            if x.device.index != self.device:
+                raise ValueError(f"input lives on cuda:{x.device.index}, this model on cuda:{self.device}")
+            if x.dtype == torch.uint8:
+                xt, fmt = x.reshape(-1, 256).contiguous(), _lib.IN_U8IQ
+            elif x.dtype == torch.int16:
+                xt, fmt = x.reshape(-1, 256).contiguous(), _lib.IN_I16
+            else:
+                xt, fmt = x.reshape(-1, 256).to(torch.float32).contiguous(), _lib.IN_F32
             n = xt.shape[0]
             out: Dict[str, object] = {}
             with torch.cuda.device(xt.device):
@@ -130,11 +189,13 @@ class CNN2Model:
                 if want_hist:
                     out["hist"] = torch.zeros((Cn,), dtype=torch.int64, device=xt.device)
                 ptr = lambda k: out[k].data_ptr() if k in out else None  # noqa: E731
-                _lib.check(lib.mdc_predict_f32(self._h.ptr, xt.data_ptr(), n, ptr("probs"), ptr("dense"),
+                _lib.check(lib.mdc_predict_raw(self._h.ptr, xt.data_ptr(), fmt, n, ptr("probs"), ptr("dense"),
                                                ptr("cls"), ptr("hist"),
                                                torch.cuda.current_stream(xt.device).cuda_stream))
+                if self.mode == "f16x3" and self.check_range and not self.range_ok():
+                    return self._tf32_twin()._run(x, want_probs, want_dense, want_cls, want_hist)
             return out
-        xa = np.ascontiguousarray(x, dtype=np.float32).reshape(-1, 256)
+        xa, fmt = _frames_of(x)
         n = xa.shape[0]
         out = {}
         if want_probs:
@@ -146,8 +207,11 @@ class CNN2Model:
         if want_hist:
             out["hist"] = np.zeros((Cn,), dtype=np.uint64)
         ptr = lambda k: out[k].ctypes.data if k in out else None  # noqa: E731
-        _lib.check(lib.mdc_predict_f32_host(self._h.ptr, xa.ctypes.data, n, ptr("probs"), ptr("dense"),
-                                            ptr("cls"), ptr("hist")))
+        rc = lib.mdc_predict_raw_host(self._h.ptr, xa.ctypes.data, fmt, n, ptr("probs"), ptr("dense"),
+                                      ptr("cls"), ptr("hist"))
+        if rc == _lib.ERR_RANGE and self.mode == "f16x3":
+            return self._tf32_twin()._run(x, want_probs, want_dense, want_cls, want_hist)
+        _lib.check(rc)
         if want_hist:
             out["hist"] = out["hist"].astype(np.int64)
         return out
@@ -166,24 +230,24 @@ class CNN2Model:
 
     def predict_async(self, x, output: str = "softmax") -> "PendingPrediction":
         """Streaming form of :meth:`predict` for host (numpy) batches: returns at once, the next batch's transfer
-        then runs under this batch's kernels; ``.result()`` waits for and returns this batch's array.  ``x`` must
-        stay unchanged until then and should be pinned (``torch.from_numpy(a).pin_memory().numpy()``); results
-        complete in submission order.  (Keras' ``predict`` has no counterpart: it is the call for a stream of
-        batches, e.g. from ``sdr.ingest_u8``.)"""
+        then runs under this batch's kernels; ``.result()`` waits for and returns this batch's array (page-locked
+        memory owned by the result).  ``x`` must stay unchanged until then; pinned input
+        (``torch.from_numpy(a).pin_memory().numpy()``) is copied by DMA straight away, pageable input is first staged
+        by the calling thread.  Results complete in submission order.  (Keras' ``predict`` has no counterpart: it is
+        the call for a stream of batches, e.g. raw uint8 I/Q from an RTL-SDR.)"""
         key = {"softmax": "probs", "dense": "dense", "argmax": "cls"}.get(output)
         if key is None:
             raise ValueError("output must be 'softmax', 'dense' or 'argmax'")
         if _is_torch(x):
             raise ValueError("predict_async takes host (numpy) batches; CUDA tensors are already asynchronous")
-        import ctypes as C
-        xa = np.ascontiguousarray(x, dtype=np.float32).reshape(-1, 256)
+        xa, fmt = _frames_of(x)
         n, Cn = xa.shape[0], self.classes
-        out = np.empty((n,), dtype=np.int32) if key == "cls" else np.empty((n, Cn), dtype=np.float32)
+        out = pinned_empty((n,), np.int32) if key == "cls" else pinned_empty((n, Cn), np.float32)
         ptr = lambda k: out.ctypes.data if k == key else None  # noqa: E731
         ticket = C.c_int64(0)
-        _lib.check(self._h._lib.mdc_predict_f32_host_async(self._h.ptr, xa.ctypes.data, n, ptr("probs"), ptr("dense"),
+        _lib.check(self._h._lib.mdc_predict_raw_host_async(self._h.ptr, xa.ctypes.data, fmt, n, ptr("probs"), ptr("dense"),
                                                            ptr("cls"), None, C.byref(ticket)))
-        return PendingPrediction(self, ticket.value, out, xa)
+        return PendingPrediction(self, ticket.value, out, xa, output)
 
     def predict_classes(self, x):
         return self.predict(x, output="argmax")
@@ -229,33 +293,46 @@ class CNN2Model:
         return self._h.launch_count()
 
     def close(self) -> None:
+        if self._fallback is not None:
+            self._fallback.close()
         self._h.close()
 
 
 class PendingPrediction:
     """Handle of one :meth:`CNN2Model.predict_async` batch."""
 
-    def __init__(self, model: CNN2Model, ticket: int, out: np.ndarray, keep_alive):
-        self._model, self._ticket, self._out, self._keep = model, ticket, out, keep_alive
+    def __init__(self, model, ticket: int, out: np.ndarray, keep_alive, output: str = ""):
+        self._model, self._ticket, self._out, self._keep, self._output = model, ticket, out, keep_alive, output
+
+    def done(self) -> bool:
+        """True once ``result()`` has been taken."""
+        return self._ticket is None
 
     def result(self) -> np.ndarray:
         if self._ticket is not None:
-            _lib.check(self._model._h._lib.mdc_host_wait(self._model._h.ptr, self._ticket))
+            rc = self._model._h._lib.mdc_host_wait(self._model._h.ptr, self._ticket)
+            if rc == _lib.ERR_RANGE and getattr(self._model, "mode", "") == "f16x3":
+                self._out = self._model._tf32_twin().predict(self._keep, output=self._output)
+            else:
+                _lib.check(rc)
             self._ticket, self._keep = None, None
         return self._out
 
 
-def tiny_cnn2(filters: int = 3, classes: int = 3, device: int = 0) -> CNN2Model:
+def tiny_cnn2(filters: int = 3, classes: int = 3, device: Optional[int] = None) -> CNN2Model:
     """The net of CNN.ipynb cell 6 (filters=3) / cnn.py-era checkpoint (filters=10)."""
     return CNN2Model("tiny", filters, classes, "fp32", device)
 
 
-def vt_cnn2(classes: int = 11, mode: str = "bf16", device: int = 0, flatten: str = "channels_last") -> CNN2Model:
-    """VT-CNN2 of the example notebook (:231-243)."""
+def vt_cnn2(classes: int = 11, mode: str = "f16x3", device: Optional[int] = None,
+            flatten: str = "channels_last") -> CNN2Model:
+    """VT-CNN2 of the example notebook (:231-243).  ``mode``: "f16x3" (default: tensor cores at fp32-level accuracy,
+    within 1e-5 of the fp64 oracle like the reference's fp32 Keras predict), "tf32x3" (the same accuracy without a
+    range restriction, half the speed), "bf16" (3x faster, ~6e-3), "fp32" (CUDA cores)."""
     return CNN2Model("vt", 0, classes, mode, device, flatten)
 
 
-def load_model(filepath: str, device: int = 0, mode: str = "fp32") -> CNN2Model:
+def load_model(filepath: str, device: Optional[int] = None, mode: str = "f16x3") -> CNN2Model:
     """Keras ``load_model``: topology from the ``model_config`` embedded in the ``.h5``
     (SURVEY.md Appendix B.1), then ``load_weights``."""
     cfg = _config_of(filepath)

@@ -22,7 +22,9 @@ def _is_torch(x) -> bool:
 
 
 class FixedPointCNN2:
-    def __init__(self, filters: int = 3, classes: int = 3, device: int = 0):
+    def __init__(self, filters: int = 3, classes: int = 3, device: Optional[int] = None):
+        from .model import default_device
+        device = default_device() if device is None else int(device)
         self.filters, self.classes, self.device = filters, classes, device
         self._h = _lib.Handle(_lib.MODEL_TINY, filters, classes, _lib.MODE_Q612, device)
         self.tables: Optional[QWeights] = None
@@ -51,6 +53,8 @@ class FixedPointCNN2:
             import torch
             if not x.is_cuda:
                 raise ValueError("torch inputs must be CUDA tensors (pass numpy for the host path)")
+            if x.device.index != self.device:
+                raise ValueError(f"input lives on cuda:{x.device.index}, this model on cuda:{self.device}")
             xt = x.reshape(-1, 256).to(torch.int32).contiguous()
             n = xt.shape[0]
             out: Dict[str, object] = {}
@@ -94,14 +98,14 @@ class FixedPointCNN2:
 
     def predict_async(self, x, output: str = "out"):
         """Streaming form of :meth:`predict` for host (numpy) batches, see ``CNN2Model.predict_async``."""
-        from .model import PendingPrediction
+        from .model import PendingPrediction, pinned_empty
         import ctypes as C
         key = {"out": "out", "pre": "pre", "argmax": "cls"}.get(output)
         if key is None:
             raise ValueError("output must be 'out', 'pre' or 'argmax'")
         xa = np.ascontiguousarray(x, dtype=np.int32).reshape(-1, 256)
         n = xa.shape[0]
-        out = np.empty((n,), dtype=np.int32) if key == "cls" else np.empty((n, self.classes), dtype=np.int32)
+        out = pinned_empty((n,), np.int32) if key == "cls" else pinned_empty((n, self.classes), np.int32)
         ptr = lambda k: out.ctypes.data if k == key else None  # noqa: E731
         ticket = C.c_int64(0)
         _lib.check(self._h._lib.mdc_predict_q612_host_async(self._h.ptr, xa.ctypes.data, n, ptr("out"), ptr("pre"),
