@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the CNN2 hot path (BASELINE.json metric: CNN2 I/Q frames/s, 2x128 frames).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mode f16x3|bf16|tf32x3|fp32]
 
 N>1 is launched by torchrun (one rank per GPU, NCCL).  A "step" is one pass of the hot path
 over one batch of 65,536 synthetic frames per GPU (BASELINE.json configs[1]: the 11-class
@@ -9,13 +9,20 @@ VT-CNN2 stack on synthetic 2x128 I/Q, batch 65536).  Frames are independent, so 
 nothing but the final class-histogram all-reduce: scaling is weak, value = frames of all
 ranks / max-over-ranks device time.
 
+The headline mode is f16x3: fp16 hi/lo-split operands on the tcgen05 tensor cores, results within 1e-5 of the fp64
+oracle - the tolerance north_star states for the reference's fp32 Keras predict (configs[1] says fp32).  The bf16 fast
+mode (6.6e-3) and the other parity-grade modes are timed in the same run under roofline.modes.
+
 One JSON line on stdout (rank 0).  Keys beyond the base contract:
-  roofline      dominant kernel (fused conv1+conv2 implicit GEMM): algorithmic FLOPs / CUDA-event time
+  roofline      dominant kernel (fused conv1+conv2 implicit GEMM): algorithmic FLOPs / CUDA-event time; plus
+                .modes (every arithmetic mode of the same workload), .sustained (a >= 2 s loop with its clocks) and
+                .other_paths (the HBM-bound rows of SURVEY section 8d - integer SV-exact, TinyCNN2 fp32, raw ingest,
+                FWHT - each with its own roofline)
   cpu_baseline  the CPU stand-in for the reference's Keras/TF predict (oracle/cnn2_torch_cpu.py)
-  e2e           same metric through the public API with pinned HOST buffers (H2D + D2H inside)
-  other_paths   the HBM-bound rows of SURVEY section 8d (integer SV-exact, TinyCNN2 fp32, FWHT),
-                each with its own roofline
-`--impl reference` times only the CPU stand-in (rank 0), on bounded samples of the same workload.
+  e2e           same metric through the public API with HOST buffers (H2D + D2H inside the timed region): the
+                streaming call on pinned f32 frames (.value), one blocking call per step (.blocking_call), the call
+                the reference makes - model.predict(pageable ndarray) (.pageable) - and raw uint8 frames (.u8_stream)
+`--impl reference` times only the CPU stand-in (rank 0) on the same 65,536-frame steps when they fit the time budget.
 """
 from __future__ import annotations
 
@@ -129,6 +136,15 @@ def cpu_vt_baseline(weights, budget_s: float = 12.0):
             "seconds": dt}
 
 
+def _reference_frames_per_step(rate: float, total_steps: int) -> int:
+    """The full 65,536-frame step when the whole run then ends within the budget (default 240 s), else a bounded
+    sample of it (multiple of the CPU batch of 256)."""
+    budget = float(os.environ.get("MDC_BENCH_REF_SECONDS", 240.0))
+    if BATCH * total_steps / rate <= budget:
+        return BATCH
+    return int(min(BATCH, max(256, rate * budget / total_steps))) // 256 * 256
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
@@ -144,9 +160,7 @@ def run_reference(args):
     t = time.perf_counter()
     m.predict(x, batch_size=256)
     rate = 256 / (time.perf_counter() - t)
-    total = args.steps + args.warmup
-    budget = float(os.environ.get("MDC_BENCH_REF_SECONDS", 120.0))        # whole run <= ~2 min
-    n = int(min(BATCH, max(256, rate * budget / total))) // 256 * 256
+    n = _reference_frames_per_step(rate, args.steps + args.warmup)
     x = synth.iq_frames(n, seed=2016)
     for _ in range(args.warmup):
         m.predict(x, batch_size=256)
@@ -155,7 +169,8 @@ def run_reference(args):
         m.predict(x, batch_size=256)
     dt = time.perf_counter() - t
     v = n * args.steps / dt
-    sample = f"{n} frames per step (bounded sample of the {BATCH}-frame batch), torch-CPU stand-in for Keras/TF-CPU predict"
+    sample = (f"{n} frames per step ({'the full batch' if n == BATCH else 'bounded sample of the ' + str(BATCH) + '-frame batch'}), "
+              "torch-CPU stand-in for Keras/TF-CPU predict")
     _emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -234,15 +249,27 @@ def hbm_path(name, handle_like, call_dev, call_host, bytes_per_unit, units, unit
     return out
 
 
+# tensor-core MMAs per product and the cuBLAS-bf16-relative rate of the MMA kind: the roofline of a mode is the
+# measured bf16 peak / (mmas / rate) in algorithmic FLOPs
+MODE_COST = {"bf16": 1.0, "f16x3": 3.0, "tf32x3": 6.0}
+MODE_ACCURACY = {
+    "f16x3": "logits within 1e-5 of the largest logit of the fp64 oracle (tests/test_gpu_vt.py): fp16 hi/lo split, 3 kind::f16 MMAs",
+    "tf32x3": "logits within 1e-5 (measured 2.6e-6): tf32 hi/lo split, 3 half-rate kind::tf32 MMAs; no range restriction",
+    "bf16": "logits within 2e-2 of the largest logit (measured 6.6e-3), argmax agreement 99.96 %",
+    "fp32": "logits within 1e-5 (measured 3.7e-6): fp32 FMA on CUDA cores",
+}
+# DRAM bytes of one conv-kernel launch at 65,536 frames from the committed ncu --set full captures
+# (dram__bytes_read.sum + dram__bytes_write.sum), not re-measured by this program
+NCU_TRAFFIC = {"bf16": (1.393e9, "profiles/r01_ncu_vt_bf16.md")}
+
+
 def run_ours(args):
+    import ctypes as C
     import torch
     import torch.distributed as dist
-    from modulationdetectioncnn_b200 import synth
-    from modulationdetectioncnn_b200.dist import allreduce_histogram, init_process_group, rank_world
-    from modulationdetectioncnn_b200.model import tiny_cnn2, vt_cnn2
-    from modulationdetectioncnn_b200.qmodel import FixedPointCNN2
-    from modulationdetectioncnn_b200.svtext import QWeights
-    from modulationdetectioncnn_b200.fwht import fwht
+    from modulationdetectioncnn_b200 import _lib, synth
+    from modulationdetectioncnn_b200.dist import allreduce_histogram, bind_to_gpu_numa_node, init_process_group, rank_world
+    from modulationdetectioncnn_b200.model import vt_cnn2
 
     rank, world, local = rank_world()
     dist_on = world > 1
@@ -250,7 +277,6 @@ def run_ours(args):
         init_process_group("nccl")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    from modulationdetectioncnn_b200.dist import bind_to_gpu_numa_node
     numa_node = bind_to_gpu_numa_node(local) if dist_on else None      # host buffers next to their GPU
     peaks = load_peaks()
 
@@ -260,6 +286,7 @@ def run_ours(args):
     model = vt_cnn2(11, mode=mode, device=local)
     model.set_weights(weights)
     batch = args.batch
+    model.reserve(batch)
     gen = torch.Generator(device=dev).manual_seed(2016 + rank)
     xs = [torch.randn((batch, 2, 128), generator=gen, device=dev, dtype=torch.float32).mul_(2.0 ** -7)
           for _ in range(N_INPUT_BUFFERS)]
@@ -267,17 +294,11 @@ def run_ours(args):
     hist = torch.zeros((11,), dtype=torch.int64, device=dev)
     lib, h = model._h._lib, model._h
     stream = torch.cuda.current_stream(dev).cuda_stream
-    from modulationdetectioncnn_b200 import _lib
 
     def step_dev(i):
         x = xs[i % N_INPUT_BUFFERS]
         _lib.check(lib.mdc_predict_f32(h.ptr, x.data_ptr(), batch, probs.data_ptr(), None, None, hist.data_ptr(), stream))
 
-    step_dev(0)
-    torch.cuda.synchronize()
-    hist.zero_()
-    launches0 = None
-    h.profile_enable(False)
     for i in range(args.warmup):
         step_dev(i)
     torch.cuda.synchronize()
@@ -293,85 +314,115 @@ def run_ours(args):
     total_hist = allreduce_histogram(hist)
     frames_all = batch * args.steps * world
     assert int(total_hist.sum()) == frames_all, (total_hist, frames_all)     # conservation over ranks
+    assert h.range_flags() == 0                                              # f16x3: nothing left the fp16 range
     value = frames_all / (ms * 1e-3)
 
-    tensor = mode in ("bf16", "tf32x3")
+    tensor = mode in MODE_COST
     flops_launch = VT_CONV_FLOP_PER_FRAME * batch * args.steps / max(klaunches, 1)
     k_avg_ms = kms / max(klaunches, 1)
     achieved = flops_launch / (k_avg_ms * 1e-3) / 1e12 if klaunches else None
-    # a 20-step timed region is ~40 ms of work: the kernel is timed in a burst, so the burst bf16 figure is the
-    # denominator (the sustained one is reported beside it).  3xTF32 issues 3 kind::tf32 MMAs (half the bf16
-    # rate) per product: its ceiling is the bf16 peak / 6 in algorithmic FLOPs.
-    # Long timed regions (hundreds of ms) run under the power cap like cuBLAS's own sustained figure: use that one there.
+    # a 20-step timed region is < 150 ms of work: the kernel is timed in a burst, so the burst bf16 figure is the
+    # denominator; long timed regions (--steps in the hundreds) run under the power cap like cuBLAS's own sustained figure
     burst = ms < 150.0
     peak_bf16 = peaks["bf16_tflops"] if burst else peaks["bf16_tflops_sustained"]
-    peak = (peak_bf16 / (6.0 if mode == "tf32x3" else 1.0)) if tensor else None
-    # DRAM bytes of one conv-kernel launch at 65,536 frames, from the ncu --set full capture summarised in
-    # profiles/r01_ncu_vt_bf16.md (dram__bytes_read.sum + dram__bytes_write.sum = 0.068 + 1.325 GB; the
-    # algorithmic bytes are 65536 x (1024 in + 21120 out) = 1.451 GB)
-    traffic = 1.393e9 if (mode == "bf16" and batch == BATCH) else None
+    peak = peak_bf16 / MODE_COST[mode] if tensor else None
+    traffic, traffic_src = NCU_TRAFFIC.get(mode, (None, None)) if batch == BATCH else (None, None)
     roofline = {"bound": "tensor", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": (achieved / peak) if (achieved and peak) else None, "traffic": traffic,
-                "frac_of_burst_peak": (achieved / peaks["bf16_tflops"]) if (achieved and mode == "bf16") else None,
-                "frac_of_sustained_peak": (achieved / peaks["bf16_tflops_sustained"]) if (achieved and mode == "bf16") else None,
-                "peak_source": peaks["source"] + ((" (cuBLAS bf16 " + ("burst" if burst else "sustained") + f": timed region {ms:.0f} ms"
-                                                    + ("; / 6 for 3xTF32)" if mode == "tf32x3" else ")")) if tensor else ""),
+                "traffic_source": (f"constant from the committed ncu capture {traffic_src}, not re-measured here"
+                                   if traffic_src else "no ncu capture of this mode's kernel yet"),
+                "peak_source": (f"{peaks['source']} cuBLAS bf16 {'burst' if burst else 'sustained'} {peak_bf16} TFLOP/s "
+                                f"(timed region {ms:.0f} ms) / {MODE_COST[mode]:g} tensor-core passes per product") if tensor else "",
                 "launches": klaunches, "avg_launch_ms": k_avg_ms,
-                "algorithmic_flop_per_frame": VT_CONV_FLOP_PER_FRAME,
+                "algorithmic_flop_per_frame": VT_CONV_FLOP_PER_FRAME, "algorithmic_flop_per_frame_whole_net": VT_FLOP_PER_FRAME,
+                "frames_per_launch": batch,
                 "kernel_share_of_step": kms / ms if ms else None,
-                "whole_net_tflops": VT_FLOP_PER_FRAME * batch * args.steps / (ms * 1e-3) / 1e12}
+                "whole_net_tflops": VT_FLOP_PER_FRAME * batch * args.steps / (ms * 1e-3) / 1e12,
+                "whole_net_frac": (VT_FLOP_PER_FRAME * batch * args.steps / (ms * 1e-3) / 1e12 / peak) if peak else None}
     if not tensor:
         roofline["note"] = "fp32 CUDA-core parity mode: no tensor-pipe peak applies; frac is null"
 
-    # ---------------- e2e through the public API, pinned host buffers
-    import ctypes as C
+    # ---------------- sustained: the same loop for >= 2 s under the power cap, with its clocks
+    sus_steps = max(args.steps, int(2200.0 / (ms / args.steps)) + 1)
+    h.profile_enable(True)
+    h.profile_read()
+    with ClockSampler(local) as clk_s:
+        sms = time_device(step_dev, sus_steps, 0, torch, dist_on)
+    skms, skl, _ = h.profile_read()
+    h.profile_enable(False)
+    s_ach = VT_CONV_FLOP_PER_FRAME * batch / (skms / max(skl, 1) * 1e-3) / 1e12 if skl else None
+    roofline["sustained"] = {
+        "value": batch * sus_steps * world / (sms * 1e-3), "unit": UNIT, "steps": sus_steps, "seconds": sms * 1e-3,
+        "ms_per_step": sms / sus_steps, "kernel_avg_launch_ms": skms / max(skl, 1), "achieved": s_ach,
+        "peak": (peaks["bf16_tflops_sustained"] / MODE_COST[mode]) if tensor else None,
+        "frac": (s_ach / (peaks["bf16_tflops_sustained"] / MODE_COST[mode])) if (tensor and s_ach) else None,
+        "clocks": clk_s.summary()}
+
+    # ---------------- e2e through the public API with HOST buffers
     xh = [torch.randn((batch, 2, 128), dtype=torch.float32).mul_(2.0 ** -7).pin_memory() for _ in range(2)]
     xh_np = [t.numpy() for t in xh]
     ph_np = [torch.empty((batch, 11), dtype=torch.float32).pin_memory().numpy() for _ in range(2)]
     hh = [torch.zeros(11, dtype=torch.int64).pin_memory().numpy().view(np.uint64) for _ in range(2)]
+    e2e_steps = max(2, min(args.steps, 10))
 
-    # (a) one blocking predict call per step
+    # (a) one blocking predict call per step, pinned buffers
     def step_host(i):
         _lib.check(lib.mdc_predict_f32_host(h.ptr, xh_np[i % 2].ctypes.data, batch, ph_np[i % 2].ctypes.data, None, None,
                                             hh[i % 2].ctypes.data))
-
-    e2e_steps = max(2, min(args.steps, 10))
     hms_sync = time_host(step_host, e2e_steps, 2, torch, dist_on)
 
     # (b) the streaming call: step i is submitted, then step i-1's results are waited for and read - every step still
-    # moves its own 64 MiB in and its probabilities out, but the next step's copies run under this step's kernels
-    pending = []
+    # moves its own frames in and its probabilities out, but the next step's copies run under this step's kernels
+    def stream_runner(bufs, fmt):
+        pending = []
 
-    def step_stream(i):
-        t = C.c_int64(0)
-        _lib.check(lib.mdc_predict_f32_host_async(h.ptr, xh_np[i % 2].ctypes.data, batch, ph_np[i % 2].ctypes.data, None, None,
-                                                  hh[i % 2].ctypes.data, C.byref(t)))
-        if pending:
-            _lib.check(lib.mdc_host_wait(h.ptr, pending.pop()))
-            assert int(hh[(i + 1) % 2].view(np.int64).sum()) == batch        # the previous step's histogram has landed
-        pending.append(t.value)
+        def run(i):
+            t = C.c_int64(0)
+            _lib.check(lib.mdc_predict_raw_host_async(h.ptr, bufs[i % 2].ctypes.data, fmt, batch, ph_np[i % 2].ctypes.data,
+                                                      None, None, hh[i % 2].ctypes.data, C.byref(t)))
+            if pending:
+                _lib.check(lib.mdc_host_wait(h.ptr, pending.pop()))
+                assert int(hh[(i + 1) % 2].view(np.int64).sum()) == batch    # the previous step's histogram has landed
+            pending.append(t.value)
+            if i == 2 + e2e_steps - 1:
+                _lib.check(lib.mdc_host_wait(h.ptr, pending.pop()))
+        return run
+    hms = time_host(stream_runner(xh_np, _lib.IN_F32), e2e_steps, 2, torch, dist_on)
+    # (c) the same stream with raw uint8 I/Q frames (256 B per frame), converted inside the conv kernel's frame load
+    u8 = [torch.randint(0, 256, (batch, 128, 2), dtype=torch.uint8).pin_memory().numpy() for _ in range(2)]
+    hms_u8 = time_host(stream_runner(u8, _lib.IN_U8IQ), e2e_steps, 2, torch, dist_on) if tensor else None
+    # (d) the call the reference makes (cnn.py:198): model.predict on an ordinary pageable ndarray, pageable result
+    xpg = [np.array(a, copy=True) for a in xh_np]
 
-    def run_stream(i):
-        step_stream(i)
-        if i == run_stream.last:
-            _lib.check(lib.mdc_host_wait(h.ptr, pending.pop()))
-    run_stream.last = 2 + e2e_steps - 1
-    hms = time_host(run_stream, e2e_steps, 2, torch, dist_on)
-    e2e = {"value": batch * e2e_steps * world / (hms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": batch * 1024,
-           "d2h_bytes_per_step": batch * 11 * 4 + 11 * 8, "steps": e2e_steps,
-           "api": "mdc_predict_f32_host_async + mdc_host_wait (CNN2Model.predict_async): step i submitted, step i-1 read back",
-           "blocking_call": {"value": batch * e2e_steps * world / (hms_sync * 1e-3), "unit": UNIT,
-                             "api": "mdc_predict_f32_host (what CNN2Model.predict(numpy) calls), one blocking call per step"}}
+    def step_pageable(i):
+        p = model.predict(xpg[i % 2], batch_size=1024)
+        assert p.shape == (batch, 11)
+    hms_pg = time_host(step_pageable, e2e_steps, 2, torch, dist_on)
+
+    def rate(t_ms):
+        return batch * e2e_steps * world / (t_ms * 1e-3)
+    d2h = batch * 11 * 4 + 11 * 8
+    e2e = {"value": rate(hms), "unit": UNIT, "h2d_bytes_per_step": batch * 1024, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+           "api": "mdc_predict_raw_host_async(MDC_IN_F32) + mdc_host_wait on pinned buffers (what CNN2Model.predict_async calls): "
+                  "step i submitted, step i-1 read back",
+           "blocking_call": {"value": rate(hms_sync), "unit": UNIT,
+                             "api": "mdc_predict_f32_host on pinned buffers, one blocking call per step"},
+           "pageable": {"value": rate(hms_pg), "unit": UNIT, "h2d_bytes_per_step": batch * 1024, "d2h_bytes_per_step": batch * 44,
+                        "api": "CNN2Model.predict(numpy ndarray in pageable memory, batch_size=1024) -> ndarray: the call "
+                               "cnn.py:198 makes; staged through the library's pinned ring by its copy threads",
+                        "host_cores": os.cpu_count()}}
+    if hms_u8:
+        e2e["u8_stream"] = {"value": rate(hms_u8), "unit": UNIT, "h2d_bytes_per_step": batch * 256, "d2h_bytes_per_step": d2h,
+                            "api": "mdc_predict_raw_host_async(MDC_IN_U8IQ): raw RTL-SDR bytes, converted in the conv kernel's frame load"}
 
     result = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": {"bf16": "bf16", "tf32x3": "tf32x3", "fp32": "f32"}[mode], "data": "synthetic",
+        "dtype": {"bf16": "bf16", "tf32x3": "tf32x3", "f16x3": "f16x3", "fp32": "f32"}[mode], "data": "synthetic",
         "config": {"workload": "VT-CNN2 11-class (BASELINE configs[1] / SURVEY C2b), 2x128 I/Q frames",
                    "frames_per_gpu_per_step": batch, "weights": "synthetic Glorot/He, Philox(1602)",
                    "input": "N(0, 2^-7) float32, torch.Generator(seed 2016+rank)", "mode": mode,
-                   "precision": "headline = the bf16 fast mode BASELINE's north_star defines; the fp32-accurate modes "
-                                "(tf32x3 on tensor cores, fp32 on CUDA cores) are timed in the same run under 'modes'",
+                   "precision": MODE_ACCURACY[mode],
                    "l2": f"{N_INPUT_BUFFERS} distinct input buffers rotated ({N_INPUT_BUFFERS * batch * 1024 >> 20} MiB > 126 MB L2)",
                    "parallelism": f"frame-sharded dp{world}, one NCCL all-reduce of int64[11] histogram",
                    "numa_node_of_rank0": numa_node},
@@ -381,24 +432,34 @@ def run_ours(args):
     # ---------------- rank 0, N=1: the other arithmetic modes of the same workload, CPU baseline, HBM-bound paths
     if rank == 0 and world == 1 and not args.skip_other:
         modes = {mode: {"value": value, "unit": UNIT, "ms_per_step": ms / args.steps, "steps": args.steps}}
-        for other, k_steps in (("bf16", 10), ("tf32x3", 5), ("fp32", 1)):
+        for other, k_steps in (("f16x3", 10), ("bf16", 20), ("tf32x3", 5), ("fp32", 1)):
             if other == mode:
                 continue
             mo = vt_cnn2(11, mode=other, device=local)
             mo.set_weights(weights)
+            mo.reserve(batch)
+            mo._h.profile_enable(True)
 
             def step_o(i, mo=mo):
                 _lib.check(lib.mdc_predict_f32(mo._h.ptr, xs[i % N_INPUT_BUFFERS].data_ptr(), batch, probs.data_ptr(), None, None,
                                                None, stream))
-            mms = time_device(step_o, k_steps, 1, torch, False)
+            time_device(step_o, 1, 1, torch, False)
+            mo._h.profile_read()
+            mms = time_device(step_o, k_steps, 0, torch, False)
+            okms, okl, okname = mo._h.profile_read()
             modes[other] = {"value": batch * k_steps / (mms * 1e-3), "unit": UNIT, "ms_per_step": mms / k_steps, "steps": k_steps}
+            if other in MODE_COST and okl:
+                o_ach = VT_CONV_FLOP_PER_FRAME * batch / (okms / okl * 1e-3) / 1e12
+                o_peak = peaks["bf16_tflops"] / MODE_COST[other]
+                modes[other]["roofline"] = {"kernel": okname, "achieved": o_ach, "peak": o_peak, "unit": "TFLOP/s",
+                                            "frac": o_ach / o_peak, "avg_launch_ms": okms / okl,
+                                            "traffic": NCU_TRAFFIC.get(other, (None, None))[0]}
             mo.close()
-        modes["bf16"]["accuracy"] = "logits within 2e-2 of the largest logit of the fp64 oracle (measured 6.6e-3)"
-        modes["tf32x3"]["accuracy"] = "logits within 1e-5 (measured 2.6e-6): tensor cores at fp32-level accuracy"
-        modes["fp32"]["accuracy"] = "logits within 1e-5 (measured 3.7e-6): fp32 FMA on CUDA cores"
-        result["modes"] = modes
+        for k in modes:
+            modes[k]["accuracy"] = MODE_ACCURACY[k]
+        roofline["modes"] = modes
         result["cpu_baseline"] = cpu_vt_baseline(weights)
-        result["other_paths"] = other_paths(torch, dev, peaks, _lib)
+        roofline["other_paths"] = other_paths(torch, dev, peaks, _lib)
     if rank == 0:
         _emit(json.dumps(result))
     if dist_on:
@@ -417,8 +478,8 @@ def other_paths(torch, dev, peaks, _lib):
     gen = torch.Generator(device=dev).manual_seed(2015)
     stream = torch.cuda.current_stream(dev).cuda_stream
 
-    # C1: integer SV-exact, N = 2^21 frames (2 GiB > L2)
-    n = 1 << 21
+    # C1: integer SV-exact, N = 2^22 frames (4 GiB of int32 frames > L2)
+    n = 1 << 22
     xq = torch.randn((n, 256), generator=gen, device=dev).mul_(32).trunc_().to(torch.int32)
     qm = FixedPointCNN2(3, 3, dev.index)
     qm.set_tables(QWeights(g["A_conv_tab"], g["A_dense_bias"], g["A_dense_tabs"]))
@@ -500,7 +561,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mode", default=os.environ.get("MDC_BENCH_MODE", "bf16"), choices=["bf16", "tf32x3", "fp32"])
+    ap.add_argument("--mode", default=os.environ.get("MDC_BENCH_MODE", "f16x3"), choices=["f16x3", "bf16", "tf32x3", "fp32"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--skip-other", action="store_true")
     args = ap.parse_args()

@@ -483,7 +483,9 @@ vt_conv_kernel(const __grid_constant__ ConvW1 w1c, const uint8_t* __restrict__ x
             *reinterpret_cast<uint4*>(orow + (rot ? ((j + 1) % 10) : j) * 16) = val;
           }
         } else {
-          // fp16 hi tile, then the lo tile kOutTile bytes further
+          // fp16 hi tile, then the lo tile kOutTile bytes further.  Only rows that are stored count for the range
+          // check: the tile's two halo rows (and rows past the last frame) are sums over whatever follows the A image
+          const bool row_live = q * 32 + lane < rows;
           uint4 oh[10], ol[10];
 #pragma unroll
           for (int c8 = 0; c8 < 10; ++c8) {
@@ -494,7 +496,7 @@ vt_conv_kernel(const __grid_constant__ ConvW1 w1c, const uint8_t* __restrict__ x
             for (int e = 0; e < 4; ++e) {
               const float ra = fmaxf(__uint_as_float(v[c8 * 8 + 2 * e]) + bv[2 * e], 0.f);
               const float rb = fmaxf(__uint_as_float(v[c8 * 8 + 2 * e + 1]) + bv[2 * e + 1], 0.f);
-              amax = fmaxf(amax, fmaxf(ra, rb));
+              amax = fmaxf(amax, row_live ? fmaxf(ra, rb) : 0.f);
               split_f16x2(ra, rb, hw[e], lw[e]);
             }
             oh[c8] = make_uint4(hw[0], hw[1], hw[2], hw[3]);

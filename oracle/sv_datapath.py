@@ -40,7 +40,8 @@ from typing import Dict, Tuple
 
 import numpy as np
 
-__all__ = ["mult_slice", "forward", "forward_pre", "simulate_rtl", "dense_rom_address"]
+__all__ = ["mult_slice", "forward", "forward_pre", "forward_deskewed_pre", "simulate_rtl", "dense_rom_address",
+           "deskewed_rom_address"]
 
 _M36 = (1 << 36) - 1
 
@@ -65,8 +66,10 @@ def dense_rom_address(F: int) -> np.ndarray:
     return 128 * np.arange(F)[:, None] + np.maximum(s - 1, 0)[None, :]
 
 
-def forward_pre(x: np.ndarray, conv_tab, dense_bias, dense_tabs) -> np.ndarray:
-    """32-bit accumulators before the final ReLU.  x int [N,256] -> int32 [N,C]."""
+def _accumulate(x: np.ndarray, conv_tab, dense_bias, dense_tabs, address: np.ndarray) -> np.ndarray:
+    """The datapath with the dense ROM address map as a parameter: ``address`` int [F,P] gives, for filter f and conv
+    position p < P, the ROM entry that multiplies conv output (f, p).  Everything else - input map, zero padding,
+    slice / bias wrap / ReLU of the conv stage, slice and 32-bit accumulate of the dense stage - is common."""
     x = np.asarray(x, dtype=np.int64).reshape(-1, 256)
     conv_tab = np.asarray(conv_tab, dtype=np.int64)
     dense_bias = np.asarray(dense_bias, dtype=np.int64)
@@ -74,20 +77,43 @@ def forward_pre(x: np.ndarray, conv_tab, dense_bias, dense_tabs) -> np.ndarray:
     N = x.shape[0]
     F = conv_tab.shape[0] // 3
     C = dense_tabs.shape[0] // 2
+    P = address.shape[1]
     xp = np.zeros((N, 2, 130), dtype=np.int64)
     xp[:, 0, 1:129] = x[:, 0:128]        # I  (test_input, sv:88-89,102)
     xp[:, 1, 1:129] = x[:, 128:256]      # Q
-    A = dense_rom_address(F)             # [F,128]
     acc = np.broadcast_to(dense_bias, (N, C)).copy()
     for f in range(F):
         w0, w1, bias = conv_tab[3 * f], conv_tab[3 * f + 1], conv_tab[3 * f + 2]
-        y = _s(mult_slice(xp[:, :, 0:128], w0, xp[:, :, 1:129], w1) + bias, 18)   # positions 0..127 only
-        y = np.where(y < 0, 0, y)        # [N,2,128]
+        y = _s(mult_slice(xp[:, :, 0:P], w0, xp[:, :, 1:P + 1], w1) + bias, 18)   # conv positions 0..P-1
+        y = np.where(y < 0, 0, y)        # [N,2,P]
         for c in range(C):
-            wi = dense_tabs[2 * c][A[f]]
-            wq = dense_tabs[2 * c + 1][A[f]]
+            wi = dense_tabs[2 * c][address[f]]
+            wq = dense_tabs[2 * c + 1][address[f]]
             acc[:, c] += mult_slice(y[:, 0, :], wi, y[:, 1, :], wq).sum(axis=1)
     return _s(acc, 32).astype(np.int32)
+
+
+def forward_pre(x: np.ndarray, conv_tab, dense_bias, dense_tabs) -> np.ndarray:
+    """32-bit accumulators before the final ReLU, as the hardware computes them: conv positions 0..127 only, ROM
+    address ``128*f + max(s-1,0)``.  x int [N,256] -> int32 [N,C]."""
+    F = np.asarray(conv_tab).shape[0] // 3
+    return _accumulate(x, conv_tab, dense_bias, dense_tabs, dense_rom_address(F))
+
+
+def deskewed_rom_address(F: int) -> np.ndarray:
+    """The address map the weight tables were LAID OUT for (``table[f*129 + p]`` =
+    ``float2fix(DenseKernel[r*387 + p*3 + f, c])``): entry ``129*f + p`` for every conv position p = 0..128."""
+    return 129 * np.arange(F)[:, None] + np.arange(129)[None, :]
+
+
+def forward_deskewed_pre(x: np.ndarray, conv_tab, dense_bias, dense_tabs) -> np.ndarray:
+    """The quantisation of the Keras net the authors intended: the SAME arithmetic primitives as ``forward_pre``
+    (``_accumulate``), with the dense ROM read at ``129*f + p`` over all 129 positions instead of the skewed
+    ``128*f + max(s-1,0)`` over 128.  Not what the hardware computes - it exists to pin slice / bias wrap / ReLU /
+    accumulate against the Keras output the reference records (12.16.testDataYunyun.txt:264, CNN.ipynb cell 18):
+    ``tests/test_oracle_int.py::test_deskewed_datapath_reproduces_recorded_keras_output``."""
+    F = np.asarray(conv_tab).shape[0] // 3
+    return _accumulate(x, conv_tab, dense_bias, dense_tabs, deskewed_rom_address(F))
 
 
 def forward(x: np.ndarray, conv_tab, dense_bias, dense_tabs) -> np.ndarray:

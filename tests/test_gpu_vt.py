@@ -372,7 +372,7 @@ def test_bf16_conv2_activations_match_bf16_emulation(vt):
     act = (bits.astype(np.uint32) << 16).view(np.float32).reshape(n, 132, 80)
     w1 = ws[0].reshape(3, 256).astype(np.float32)
     w2 = _bf16_round(ws[2]).reshape(1536, 80).astype(np.float64)
-    worst = 0.0
+    wants = []
     for s in range(0, n, 256):
         xs = x[s:s + 256]
         k = xs.shape[0]
@@ -383,11 +383,12 @@ def test_bf16_conv2_activations_match_bf16_emulation(vt):
         ap = np.zeros((k, 2, 134, 256), np.float32)
         ap[:, :, 2:132] = a
         cols = np.concatenate([ap[:, r, j:j + 132, :] for r in range(2) for j in range(3)], axis=-1).astype(np.float64)
-        want = _bf16_round(np.maximum(cols @ w2 + ws[3].astype(np.float64), 0).astype(np.float32))
-        d = np.abs(act[s:s + 256] - want)
-        tol = 2.0 ** -7 * np.abs(want) + 1e-4 * np.abs(want).max()       # 1 bf16 ulp + cancellation slack
-        assert not (d > tol).any(), (s, float(d.max()))
-        worst = max(worst, float(d.max()))
+        wants.append(_bf16_round(np.maximum(cols @ w2 + ws[3].astype(np.float64), 0).astype(np.float32)))
+    want = np.concatenate(wants)
+    d = np.abs(act - want)
+    tol = 2.0 ** -7 * np.abs(want) + 1e-4 * np.abs(want).max()       # 1 bf16 ulp + cancellation slack
+    bad = d > tol
+    assert not bad.any(), (int(bad.sum()), np.argwhere(bad)[:5].tolist(), float(d.max()))
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -456,7 +457,8 @@ def test_predict_async_returns_before_the_batch_is_done(vt):
     m.set_weights(_wlist(w))
     n = 4 * 65536                                                                # ~20 ms of kernels
     xp = torch.from_numpy(np.tile(x, (n // x.shape[0] + 1, 1, 1))[:n].copy()).pin_memory().numpy()
-    m.predict_async(xp[:65536]).result()                                          # warm-up: buffers, work space
+    for _ in range(2):
+        m.predict_async(xp).result()                   # warm-up: work space, device slots, the pinned result block
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     p = m.predict_async(xp)

@@ -116,3 +116,71 @@ def test_unused_rom_entries_do_not_matter(qsets):
     for a in (127, 255, 383, 384, 385, 386):
         dt[:, a] = 12345
     assert np.array_equal(sv.forward_pre(x, ct, db, dt), base)
+
+
+def test_deskewed_address_map_is_the_only_difference():
+    """forward_pre and forward_deskewed_pre run the same arithmetic (sv._accumulate); only the ROM address map differs."""
+    A, D = sv.dense_rom_address(3), sv.deskewed_rom_address(3)
+    assert A.shape == (3, 128) and D.shape == (3, 129)
+    assert D[0].tolist() == list(range(129)) and D[2, 128] == 386          # every table entry used exactly once
+    assert sorted(D.reshape(-1).tolist()) == list(range(387))
+    g = np.random.default_rng(1)
+    x = g.integers(-(1 << 17), 1 << 17, (8, 256))
+    ct = g.integers(-(1 << 17), 1 << 17, 9)
+    db = g.integers(-(1 << 17), 1 << 17, 3)
+    dt = g.integers(-(1 << 17), 1 << 17, (6, 387))
+    assert np.array_equal(sv._accumulate(x, ct, db, dt, A), sv.forward_pre(x, ct, db, dt))
+    assert np.array_equal(sv._accumulate(x, ct, db, dt, D), sv.forward_deskewed_pre(x, ct, db, dt))
+    assert not np.array_equal(sv.forward_pre(x, ct, db, dt), sv.forward_deskewed_pre(x, ct, db, dt))
+
+
+def test_deskewed_datapath_reproduces_recorded_keras_output(golden, qsets, h5w):
+    """PIN of the integer primitives (slice, 18-bit bias wrap, ReLU, 32-bit accumulate) to a number the reference
+    records.  With the dense ROM read at the address the tables were laid out for (129 f + p, all 129 positions) the
+    integer datapath must be the Q6.12 quantisation of the Keras net, i.e. reproduce the Dense+ReLU output Keras
+    printed for the two recorded frames (12.16.testDataYunyun.txt:2,264; CNN.ipynb cell 18) to within quantisation
+    error.  The bound, per class, in output LSBs (2^-12):
+        387 floors of the dense slice (each in (-1, 0])          -> 387
+      + truncated dense weights, |w*4096 - wq| < 1 per entry    -> sum_p (yI + yQ) / 4096
+      + conv-stage error |dy| < 2 + (|x_p| + |x_p+1|) / 4096 (two truncated weights, truncated bias, one floor)
+        carried through the dense weights                        -> sum |wq| / 4096 * |dy|
+    What is left unpinned after this is the skew itself, which is read directly off cnn_test_latest1.sv:336,351-378.
+    One table entry is not a quantisation of the checkpoint: rom_dense_q_class3[373] was hand-edited to -16.0 (-65536;
+    float2fix of the tiny negative h5 weight -1.38e-4 emits a 19-bit literal); the pin uses the value
+    float2fix's formula gives for it (0) and checks the hand edit's effect separately."""
+    from oracle import cnn2_float as cf
+    kat = golden["kat"]
+    vec = golden["vectors"]["vectors"]
+    ct, db, dt = (np.array(a) for a in qsets["A"])
+    w = h5w["A_3conv"]
+    r, p, f, c = 1, 115, 2, 2                                    # table class3-Q, entry 129*2 + 115 = 373
+    assert dt[2 * c + r][129 * f + p] == -65536
+    true_w = float(w[2][r * 387 + p * 3 + f, c])
+    assert -1 < true_w * 4096 < 0                                 # the float2fix corner case
+    dt_q = dt.copy()
+    dt_q[2 * c + r][129 * f + p] = 0
+    for idx_key, out_key in (("vector_index_3samples", "keras_dense_3samples"),
+                             ("vector_index_64samples", "keras_dense_64samples")):
+        x = vec[kat[idx_key]]
+        got = np.maximum(sv.forward_deskewed_pre(x, ct, db, dt_q)[0], 0).astype(np.float64)
+        xf = (x.astype(np.float64) / 4096).reshape(1, 2, 128)
+        z = cf.tiny_cnn2_forward(xf, *w, output="dense")[0] * 4096          # fp64 Keras restatement, same inputs
+        y = cf.tiny_cnn2_forward(xf, *w, output="conv")[0] * 4096           # [2,129,3] conv outputs in LSBs
+        xi = np.abs(x.astype(np.float64)).reshape(2, 128)
+        xpad = np.zeros((2, 130))
+        xpad[:, 1:129] = xi
+        dy = 2 + (xpad[:, 0:129] + xpad[:, 1:130]) / 4096                   # [2,129]
+        for cls in range(3):
+            wabs = np.stack([np.abs(dt_q[2 * cls + rr].reshape(3, 129)).T for rr in range(2)])   # [2,129,3]
+            bound = 387 + y.sum() / 4096 + (wabs / 4096 * dy[:, :, None]).sum() + 1
+            assert abs(got[cls] - max(z[cls], 0)) <= bound, (out_key, cls, got[cls], z[cls], bound)
+            assert bound < 0.15 * z.max()                                   # the worst case is 13 % of the largest output,
+            assert abs(got[cls] - max(z[cls], 0)) < 0.025 * z.max()         # the error measured here is 2 % (-274 LSB)
+        # and against the digits Keras printed (its inputs were the unquantised floats: ~3 digits, test_oracle_float)
+        keras = np.array(kat[out_key]) * 4096
+        assert np.abs(got - keras).max() < 0.05 * keras.max(), (got, keras)
+    # the hand edit: frame #1 has zero samples at p = 115, so the conv output there is the ReLU'd conv bias (241) and
+    # the deployed ROM moves class 3 by slice(241 * -65536) = -3856
+    x = vec[kat["vector_index_64samples"]]
+    d_rom = sv.forward_deskewed_pre(x, ct, db, dt)[0] - sv.forward_deskewed_pre(x, ct, db, dt_q)[0]
+    assert d_rom.tolist() == [0, 0, (241 * -65536) >> 12]
