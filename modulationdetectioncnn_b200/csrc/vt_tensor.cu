@@ -55,7 +55,6 @@ enum { kConvBF16 = 0, kConvTF32 = 1, kConvF16 = 2 };
 // for the single-CTA M = 128 x N = 80 shape, tools/umma_rate.cu / tools/umma2_probe.cu).
 constexpr int kGroups = 4;                // 16-B K groups per chunk image: g = 2 * (channel block) + input row
 constexpr int kBHalf = 40;                // W2 output channels held by each CTA of the pair
-constexpr int kBLbo = kBHalf * 16;        // bytes between K groups of the B image
 constexpr int kXFrames = 4;               // frames a super-tile's tape rows can touch
 constexpr int kOutTile = 128 * 160;       // one 128 x 80 tile of 16-bit outputs
 constexpr int kProdWarp0 = 6;
@@ -73,9 +72,12 @@ constexpr int kProdWarp0 = 6;
 //   tf32x3: accumulator 0 takes the two small cross terms (lo*hi, hi*lo) of every K step, accumulators 1..5 the
 //           hi*hi terms of chunks c = a - 1 (mod 5) - at most 42 truncating adds each; single-buffered
 //           (6 x 80 = 480 of 512 columns: the MMA warp waits while the epilogue reads, ~4 % of a tile's 576 MMAs)
-//   f16x3:  accumulator 0 takes the cross terms (operand lo parts carry a factor 2^11, undone in the epilogue),
-//           accumulators 1, 2 the hi*hi terms of even / odd chunks - 48 truncating adds each; 3 x 80 = 240
-//           columns, double-buffered, so the next tile's MMAs run under the epilogue
+//   f16x3:  the B image of a CTA holds, per tap and K group, the hi rows of its 40 output channels followed by their
+//           lo rows (which carry a factor 2^11, undone in the epilogue), so ONE N = 160 MMA A_hi x [B_hi | B_lo]
+//           yields hi*hi and hi*lo - A_hi is fetched from shared memory once for both, the N = 80 shape is
+//           operand-fetch-bound - into accumulator D1 (160 columns: per CTA half 40 hi*hi then 40 hi*lo), and an
+//           N = 80 MMA A_lo x B_hi the lo*hi term into D2 (80 columns).  The hi*hi chain is 96 truncating adds
+//           (~1.4e-6 low); 240 columns, double-buffered, so the next tile's MMAs run under the epilogue
 template <int MODE>
 struct ConvCfg {
   static constexpr bool kSplit = MODE != kConvBF16;        // hi / lo operand images, three MMAs per product
@@ -84,7 +86,12 @@ struct ConvCfg {
   static constexpr int kTapeRows = 128 * kNT;              // tape rows staged per super-tile
   static constexpr int kOutRows = kTapeRows - 2;           // conv2 rows produced per super-tile (2-row halo)
   static constexpr int kALbo = kTapeRows * 16;             // bytes between K groups of the A image
-  static constexpr int kProdWarps = kTapeRows / 32;        // one tape row per producer thread
+  // conv1 producers: one tape row per thread; f16x3 puts TWO threads on a row (8 of the chunk's 16 channels each):
+  // the hi/lo split triples the per-value work while a chunk's MMAs take no longer than in bf16 mode, and with one
+  // warp per scheduler the producers, not the tensor pipe, set the pace (measured 1,175 cycles per chunk)
+  static constexpr int kProdSplit = MODE == kConvF16 ? 2 : 1;
+  static constexpr int kProdWarps = kTapeRows / 32 * kProdSplit;
+  static constexpr int kProdUnroll = MODE == kConvF16 ? 1 : 256 / (kWide ? 8 : 16);   // producers' chunk loop
   static constexpr int kThreads = (kProdWarp0 + kProdWarps) * 32;   // TMA, MMA, 4 epilogue, producers
   static constexpr int kAccBufs = MODE == kConvTF32 ? 1 : 2;        // accumulator buffers in TMEM
   static constexpr int kAccSplit = MODE == kConvBF16 ? 1 : (MODE == kConvTF32 ? 6 : 3);   // accumulators per tile
@@ -95,8 +102,11 @@ struct ConvCfg {
   static constexpr int kStages = MODE == kConvF16 ? 4 : 5;
   static constexpr int kAImg = kGroups * kALbo;            // bf16 24,576; split modes 8,192
   static constexpr int kASlot = kImgs * kAImg;
-  static constexpr int kBImg = 3 * kGroups * kBLbo;        // 7,680: [tap][group][40][16 B]
-  static constexpr int kBSlot = kImgs * kBImg;
+  static constexpr int kBRows = MODE == kConvF16 ? 2 * kBHalf : kBHalf;   // f16x3: 40 hi rows then 40 lo rows
+  static constexpr int kBLbo = kBRows * 16;                // bytes between K groups of the B image
+  static constexpr int kBImgs = MODE == kConvTF32 ? 2 : 1; // tf32x3: separate hi and lo images
+  static constexpr int kBImg = 3 * kGroups * kBLbo;        // [tap][group][rows][16 B]: 7,680 (f16x3 15,360)
+  static constexpr int kBSlot = kBImgs * kBImg;
   static constexpr int kOutImgs = MODE == kConvTF32 ? 0 : kImgs;    // staged 16-bit output tiles per 128 rows
   // shared memory map
   static constexpr int a = 0;
@@ -136,7 +146,17 @@ __device__ __forceinline__ void split_f16x2(float r0, float r1, uint32_t& hi, ui
   hi = cvt_f16x2_sat(r1, r0);
   float f0, f1;
   unpack_f16x2(hi, f0, f1);
-  lo = cvt_f16x2_sat((r1 - f1) * 2048.f, (r0 - f0) * 2048.f);
+  // (r - f) * 2^11 as two packed ops (exact: a power-of-two scale and an exact difference)
+  uint64_t rr, ff, k, t;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rr) : "f"(r0), "f"(r1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ff) : "f"(f0), "f"(f1));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(k) : "f"(2048.f));
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(t) : "l"(rr), "l"(k));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(k) : "f"(-2048.f));
+  t = fma2_u(ff, k, t);
+  float t0, t1;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(t0), "=f"(t1) : "l"(t));
+  lo = cvt_f16x2_sat(t1, t0);
 }
 
 // conv1 weights travel as a kernel parameter (constant bank): with the chunk loop unrolled every
@@ -223,7 +243,7 @@ vt_conv_kernel(const __grid_constant__ ConvW1 w1c, const uint8_t* __restrict__ x
   constexpr bool kSplit = ConvSmem::kSplit;
   constexpr int kStages = ConvSmem::kStages, kChunks = ConvSmem::kChunks;
   constexpr int kASlot = ConvSmem::kASlot, kBSlot = ConvSmem::kBSlot, kAImg = ConvSmem::kAImg, kBImg = ConvSmem::kBImg;
-  constexpr int kNT = ConvSmem::kNT, kOutRows = ConvSmem::kOutRows, kALbo = ConvSmem::kALbo;
+  constexpr int kNT = ConvSmem::kNT, kOutRows = ConvSmem::kOutRows, kALbo = ConvSmem::kALbo, kBLbo = ConvSmem::kBLbo;
   constexpr int kProdWarps = ConvSmem::kProdWarps, kConvThreads = ConvSmem::kThreads, kAccCols = ConvSmem::kAccCols;
   constexpr int kAccBufs = ConvSmem::kAccBufs;
   extern __shared__ __align__(128) uint8_t smem[];
@@ -304,6 +324,7 @@ vt_conv_kernel(const __grid_constant__ ConvW1 w1c, const uint8_t* __restrict__ x
     if (rank == 0) {
       const uint32_t idesc = MODE == kConvTF32 ? make_idesc_tf32(256, 80)
                                                : (MODE == kConvF16 ? make_idesc_f16(256, 80) : make_idesc_bf16(256, 80));
+      const uint32_t idesc160 = make_idesc_f16(256, 160);    // f16x3: A_hi x [B_hi | B_lo]
       const uint32_t a_base = smem_u32(smem + ConvSmem::a), b_base = smem_u32(smem + ConvSmem::b);
       constexpr uint32_t hi = smem_desc_hi(128, 0);
       for (long long base = st_first; base < num_st; base += st_step, ++k) {
@@ -318,10 +339,9 @@ vt_conv_kernel(const __grid_constant__ ConvW1 w1c, const uint8_t* __restrict__ x
           if (elect_one()) {
             const uint32_t a_lo = smem_desc_lo(a_base + s * kASlot, kALbo);
             const uint32_t b_lo = smem_desc_lo(b_base + s * kBSlot, kBLbo);
-            // split modes: the hi*hi terms of chunk c go to their own accumulator (see ConvCfg), the cross
-            // terms to accumulator 0
-            const uint32_t acc_hh = acc + (MODE == kConvTF32 ? (1 + c % 5) : (1 + (c & 1))) * 80;
-            const bool hh_first_chunk = MODE == kConvTF32 ? (c < 5) : (c < 2);
+            // tf32x3: the hi*hi terms of chunk c go to accumulator 1 + c % 5, the cross terms to accumulator 0
+            const uint32_t acc_hh = acc + (1 + c % 5) * 80;
+            const bool hh_first_chunk = c < 5;
 #pragma unroll
             for (int t = 0; t < kNT; ++t) {
 #pragma unroll
@@ -336,16 +356,17 @@ vt_conv_kernel(const __grid_constant__ ConvW1 w1c, const uint8_t* __restrict__ x
                   } else {
                     constexpr uint32_t al = kAImg >> 4, bl = kBImg >> 4;   // offsets of the lo images
                     const uint64_t ah_d = desc64(a_lo + ao, hi), al_d = desc64(a_lo + ao + al, hi);
-                    const uint64_t bh_d = desc64(b_lo + bo, hi), bl_d = desc64(b_lo + bo + bl, hi);
-                    const uint32_t hh_acc = (!hh_first_chunk) || (ks | j) != 0;
+                    const uint64_t bh_d = desc64(b_lo + bo, hi);
                     if (MODE == kConvTF32) {
+                      const uint64_t bl_d = desc64(b_lo + bo + bl, hi);
                       mma_tf32_ss_pair(acc, al_d, bh_d, idesc, (c | ks | j) != 0);
                       mma_tf32_ss_pair(acc, ah_d, bl_d, idesc, 1);
-                      mma_tf32_ss_pair(acc_hh, ah_d, bh_d, idesc, hh_acc);
+                      mma_tf32_ss_pair(acc_hh, ah_d, bh_d, idesc, (!hh_first_chunk) || (ks | j) != 0);
                     } else {
-                      mma_f16_ss_pair(acc, al_d, bh_d, idesc, (c | ks | j) != 0);
-                      mma_f16_ss_pair(acc, ah_d, bl_d, idesc, 1);
-                      mma_f16_ss_pair(acc_hh, ah_d, bh_d, idesc, hh_acc);
+                      // D1 (160 columns) += A_hi x [B_hi | B_lo]; D2 (80 columns) += A_lo x B_hi: the same B start
+                      // address, 80 rows per CTA for the first, the leading 40 (hi) rows for the second
+                      mma_f16_ss_pair(acc, ah_d, bh_d, idesc160, (c | ks | j) != 0);
+                      mma_f16_ss_pair(acc + 160, al_d, bh_d, idesc, (c | ks | j) != 0);
                     }
                   }
                 }
@@ -413,17 +434,20 @@ vt_conv_kernel(const __grid_constant__ ConvW1 w1c, const uint8_t* __restrict__ x
             }
           }
         } else {
-          // (even-chunk hi*hi + odd-chunk hi*hi) + 2^-11 x cross terms, fp32 round-to-nearest
+          // hi*hi + 2^-11 x (hi*lo + lo*hi), fp32 round-to-nearest.  Output channels 40 hf + i, i < 40, sit at D1
+          // columns 80 hf + i (hi*hi) and 80 hf + 40 + i (hi*lo), and at D2 column 160 + 40 hf + i (lo*hi)
 #pragma unroll
-          for (int cc = 0; cc < 5; ++cc) {
-            uint32_t p[3][16];
-#pragma unroll
-            for (int a = 0; a < 3; ++a) tmem_ld16(tbase + a * 80 + cc * 16, p[a]);
+          for (int o8 = 0; o8 < 10; ++o8) {
+            const int d1 = 80 * (o8 / 5) + 8 * (o8 % 5);
+            uint32_t hh[8], hl[8], lh[8];
+            tmem_ld8(tbase + d1, hh);
+            tmem_ld8(tbase + d1 + 40, hl);
+            tmem_ld8(tbase + 160 + 8 * o8, lh);
             tmem_ld_wait();
 #pragma unroll
-            for (int e = 0; e < 16; ++e)
-              v[cc * 16 + e] = __float_as_uint(fmaf(__uint_as_float(p[0][e]), 1.f / 2048.f,
-                                                    __uint_as_float(p[1][e]) + __uint_as_float(p[2][e])));
+            for (int e = 0; e < 8; ++e)
+              v[o8 * 8 + e] = __float_as_uint(fmaf(__uint_as_float(hl[e]) + __uint_as_float(lh[e]), 1.f / 2048.f,
+                                                    __uint_as_float(hh[e])));
           }
         }
         if (t == kNT - 1) {                       // whole buffer read: hand it back to the MMA warp
@@ -532,7 +556,8 @@ vt_conv_kernel(const __grid_constant__ ConvW1 w1c, const uint8_t* __restrict__ x
     // One tape row per thread; a chunk is kCC channels x {I row, Q row}; weights come from the
     // constant bank (uniform registers), inputs stay in registers for the whole super-tile.
     const int pw = warp - kProdWarp0;
-    const int row = pw * 32 + lane;
+    const int row = (pw % (kProdWarps / ConvSmem::kProdSplit)) * 32 + lane;
+    const int phalf = pw / (kProdWarps / ConvSmem::kProdSplit);      // f16x3: which 8 of the chunk's 16 channels
     uint32_t it = 0, k = 0;
     float xmax = 0.f;
     for (long long base = st_first; base < num_st; base += st_step, ++k) {
@@ -560,7 +585,11 @@ vt_conv_kernel(const __grid_constant__ ConvW1 w1c, const uint8_t* __restrict__ x
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&x_empty[xb]);
-#pragma unroll
+      // bf16 / tf32x3: fully unrolled, every conv1 weight an immediate constant-bank operand.  f16x3: NOT unrolled -
+      // with the split's conversions the unrolled loop is ~65 KB of code executed by 8 warps next to the epilogue's,
+      // and a third of the producers' samples sat in instruction-fetch stalls (ncu: stall_no_inst); the weights are
+      // fetched through uniform loads at (c, phalf)-relative offsets instead
+#pragma unroll (ConvSmem::kProdUnroll)
       for (int c = 0; c < kChunks; ++c, ++it) {
         // compute the chunk into registers first: nothing here depends on the stage being free
         uint4 o[ConvSmem::kImgs * kGroups];
@@ -572,12 +601,10 @@ vt_conv_kernel(const __grid_constant__ ConvW1 w1c, const uint8_t* __restrict__ x
             o[2 * hc + 1] = conv1_item(xd[1][0], xd[1][1], xd[1][2], w, m);
           }
         } else if (MODE == kConvF16) {
-#pragma unroll
-          for (int hc = 0; hc < 2; ++hc) {
-            const unsigned long long* w = &w1c.v[(c * 2 + hc) * 16];
-            conv1_item_f16(xd[0][0], xd[0][1], xd[0][2], w, m, o[2 * hc], o[kGroups + 2 * hc]);
-            conv1_item_f16(xd[1][0], xd[1][1], xd[1][2], w, m, o[2 * hc + 1], o[kGroups + 2 * hc + 1]);
-          }
+          // this thread's channel block only: o[0], o[1] = hi of (block, I row), (block, Q row); o[2], o[3] = lo
+          const unsigned long long* w = &w1c.v[(c * 2 + phalf) * 16];
+          conv1_item_f16(xd[0][0], xd[0][1], xd[0][2], w, m, o[0], o[2]);
+          conv1_item_f16(xd[1][0], xd[1][1], xd[1][2], w, m, o[1], o[3]);
         } else {
           const unsigned long long* w = &w1c.v[c * 16];       // chunk c = channels 8c .. 8c+7
 #pragma unroll
@@ -596,8 +623,17 @@ vt_conv_kernel(const __grid_constant__ ConvW1 w1c, const uint8_t* __restrict__ x
         const uint32_t s = it % kStages, ph = (it / kStages) & 1;
         mbar_wait(&empty[s], ph ^ 1);
         uint8_t* arow = smem + ConvSmem::a + s * kASlot + row * 16;
+        if (MODE == kConvF16) {
+          // groups 2 phalf, 2 phalf + 1 of the hi image and of the lo image
+          uint8_t* ab = arow + 2 * phalf * kALbo;
+          *reinterpret_cast<uint4*>(ab) = o[0];
+          *reinterpret_cast<uint4*>(ab + kALbo) = o[1];
+          *reinterpret_cast<uint4*>(ab + kAImg) = o[2];
+          *reinterpret_cast<uint4*>(ab + kAImg + kALbo) = o[3];
+        } else {
 #pragma unroll
-        for (int g = 0; g < ConvSmem::kImgs * kGroups; ++g) *reinterpret_cast<uint4*>(arow + g * kALbo) = o[g];
+          for (int g = 0; g < ConvSmem::kImgs * kGroups; ++g) *reinterpret_cast<uint4*>(arow + g * kALbo) = o[g];
+        }
       }
     }
     if (it > 0) {
@@ -1234,13 +1270,16 @@ static int conv_mode_of(const mdc_handle_s* h) {
   return h->mode == MDC_MODE_TF32X3 ? kConvTF32 : (h->mode == MDC_MODE_F16X3 ? kConvF16 : kConvBF16);
 }
 
-// conv2 image of one split/unsplit mode: [chunk][pair rank][hi/lo][tap][group][40 out][16 B]; chunk c = conv1 channels
-// kCC c .. kCC c + kCC - 1, group g = 2*(channel block) + input row, rank h holds output channels
-// 40h..40h+39 (Keras (2,3,256,80) = [r][j][ch][o]).  16-bit modes: 8 values per group; tf32x3: 4 fp32 per group.
+// conv2 image of one mode: [chunk][pair rank][image][tap][group][rows][16 B]; chunk c = conv1 channels
+// kCC c .. kCC c + kCC - 1, group g = 2*(channel block) + input row, rank h holds output channels 40h..40h+39
+// (Keras (2,3,256,80) = [r][j][ch][o]).  16-bit modes: 8 values per group; tf32x3: 4 fp32 per group.
+// bf16: one image of 40 rows; tf32x3: a hi image and a lo image of 40 rows; f16x3: one image of 80 rows, the 40 hi rows
+// then the 40 lo rows.  put(value, hi, lo) stores the split value.
 template <int MODE, class Elem, class Put>
 static void build_w2_image(const float* w2, std::vector<Elem>& img, Put put) {
   using Cfg = ConvCfg<MODE>;
   constexpr int per = 16 / (int)sizeof(Elem);
+  constexpr size_t lo_off = MODE == kConvTF32 ? Cfg::kBImg / sizeof(Elem) : (size_t)kBHalf * per;
   img.assign((size_t)Cfg::kChunks * 2 * Cfg::kBSlot / sizeof(Elem), Elem());
   for (int c = 0; c < Cfg::kChunks; ++c)
     for (int hf = 0; hf < 2; ++hf)
@@ -1250,8 +1289,8 @@ static void build_w2_image(const float* w2, std::vector<Elem>& img, Put put) {
             for (int e = 0; e < per; ++e) {
               const int r = g & 1, ch = c * Cfg::kCC + (g >> 1) * per + e, o = hf * kBHalf + oo;
               const size_t base = (size_t)(c * 2 + hf) * (Cfg::kBSlot / sizeof(Elem)) +
-                                  ((size_t)(j * kGroups + g) * kBHalf + oo) * per + e;
-              put(w2[((size_t)(r * 3 + j) * 256 + ch) * 80 + o], img[base], img.data() + base + Cfg::kBImg / sizeof(Elem));
+                                  ((size_t)(j * kGroups + g) * Cfg::kBRows + oo) * per + e;
+              put(w2[((size_t)(r * 3 + j) * 256 + ch) * 80 + o], img[base], img.data() + base + lo_off);
             }
 }
 
