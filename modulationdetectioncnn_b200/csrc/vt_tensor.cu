@@ -1018,8 +1018,13 @@ vt_dense_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_
 
 // ------------------------------------------------------------------------------------------
 // dense1 in fp16 hi/lo split (MDC_MODE_F16X3): act = act_hi + 2^-11 act_lo, W3 = W3_hi + 2^-11 W3_lo (fp16 words),
-// three kind::f16 MMAs per K step at the full 16-bit rate.  Same tile and stage geometry as the 3xTF32 kernel above
-// (128 frames x 256 outputs, 96 KB stages of A hi/lo + B hi/lo, CTAs in multicast pairs) with K blocks of 64 values.
+// three kind::f16 MMAs per K step at the full 16-bit rate.  128 frames x 256 outputs per CTA, K blocks of 64 values.
+//
+// CTA pairs (cluster of 2, cta_group::2, M = 256): each CTA owns a frame tile - its A stages, its accumulators, its
+// epilogue - and HALF of every W3 block (128 of the 256 output rows, hi and lo); the leader issues one M = 256 x
+// N = 256 MMA per product for the pair.  Against one-CTA MMAs with multicast W3 halves (the 3xTF32 kernel below) a
+// K block costs each SM 64 KB of TMA writes and 96 KB of operand reads instead of 96 + 144 KB: the one-CTA form was
+// shared-memory-bound (1,875 cycles of traffic per block against 1,536 of math, tensor pipe 64 % active).
 //
 // TMEM: columns 0..255 take the hi*hi products, columns 256..511 the two cross terms (which carry a factor 2^11).
 // The cross accumulator runs over the whole K range - it is 2^-11 of the result, its truncation does not matter -
@@ -1032,7 +1037,21 @@ constexpr int kHK = 64;                            // fp16 values per K block (1
 constexpr int kHKBlocks = kVtFlat / kHK;           // 165
 constexpr int kHRunBlocks = 11;                    // K blocks per hi*hi run: 44 MMAs
 constexpr int kHRuns = kHKBlocks / kHRunBlocks;    // 15
+constexpr int kHStages = 3;
+constexpr int kHTile = 128 * 128;                  // 128 rows x 128 B: one A (hi or lo) or half-B (hi or lo) tile
+constexpr int kHStageBytes = 4 * kHTile;           // A hi, A lo, B-half hi, B-half lo = 64 KB
 static_assert(kVtFlat % kHK == 0 && kHKBlocks % kHRunBlocks == 0, "K blocks / runs must tile K");
+
+struct DenseF16Smem {
+  static constexpr int stages = 0;
+  static constexpr int b3 = kHStages * kHStageBytes;
+  static constexpr int bars = b3 + 1024;
+  // full[S], empty[S], hh_full, hh_empty, cross_empty
+  static constexpr int nbars = 2 * kHStages + 3;
+  static constexpr int tmem_slot = bars + nbars * 8;
+  static constexpr int total = tmem_slot + 16 + 1024;   // + slack for the 1024 B alignment
+};
+static_assert(DenseF16Smem::total <= 232448, "f16x3 dense kernel shared memory exceeds 227 KB");
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDenseT32Threads, 1)
 vt_dense_f16x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
@@ -1040,107 +1059,128 @@ vt_dense_f16x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_c
                       const float* __restrict__ b3g, float* __restrict__ hbuf, long long n, int num_tiles) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DenseT32Smem::bars);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DenseF16Smem::bars);
   uint64_t* full = bars;
-  uint64_t* empty = bars + kTStages;
-  uint64_t* hh_full = bars + 2 * kTStages;      // a run of hi*hi MMAs (and, at the last run, the cross sums) is complete
-  uint64_t* hh_empty = hh_full + 1;             // the epilogue warps have folded it into their registers
-  uint64_t* cross_empty = hh_full + 2;          // the epilogue warps have read the tile's cross sums
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + DenseT32Smem::tmem_slot);
+  uint64_t* empty = bars + kHStages;
+  uint64_t* hh_full = bars + 2 * kHStages;      // a run of hi*hi MMAs (and, at the last run, the cross sums) is complete
+  uint64_t* hh_empty = hh_full + 1;             // (leader's) both CTAs' epilogue warps have folded it into their registers
+  uint64_t* cross_empty = hh_full + 2;          // (leader's) both CTAs' epilogue warps have read the tile's cross sums
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + DenseF16Smem::tmem_slot);
   const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
-  const uint32_t rank = cluster_ctarank();
+  const uint32_t rank = cluster_ctarank();      // 0 = leader (issues the pair's MMAs)
   // the pair walks tiles 2 i and 2 i + 1 in lockstep (a trailing odd tile is all out-of-range rows: zero-filled
   // loads, no stores)
   const int tile_first = 2 * (int)cluster_id_x() + (int)rank, tile_step = 2 * (int)cluster_count_x();
   const int pair_iters = (num_tiles + 1) / 2;       // iterations of pair p: tiles 2 p, 2 p + 1
 
-  for (int i = tid; i < 256; i += kDenseT32Threads) reinterpret_cast<float*>(smem + DenseT32Smem::b3)[i] = b3g[i];
+  for (int i = tid; i < 256; i += kDenseT32Threads) reinterpret_cast<float*>(smem + DenseF16Smem::b3)[i] = b3g[i];
   if (tid == 0) {
-    for (int s = 0; s < kTStages; ++s) {
-      mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 2);                   // this CTA's MMAs and the peer's (its multicast writes land here too)
+    for (int s = 0; s < kHStages; ++s) {
+      mbar_init(&full[s], rank == 0 ? 2 : 1);    // own TMA (+ on the leader: the peer's relay once ITS stage is full)
+      mbar_init(&empty[s], 1);
     }
     mbar_init(hh_full, 1);
-    mbar_init(hh_empty, kTEpiWarps);
-    mbar_init(cross_empty, kTEpiWarps);
+    mbar_init(hh_empty, 2 * kTEpiWarps);
+    mbar_init(cross_empty, 2 * kTEpiWarps);
     fence_barrier_init();
     prefetch_tensormap(&map_ah);
     prefetch_tensormap(&map_al);
     prefetch_tensormap(&map_bh);
     prefetch_tensormap(&map_bl);
   }
-  if (warp == 0) tmem_alloc<512>(tmem_slot);
+  if (warp == 0) tmem_alloc_pair<512>(tmem_slot);
   tc_fence_before_sync();
   __syncthreads();
-  cluster_sync_all();                            // the peer's barriers exist before anything is multicast at them
+  cluster_sync_all();
   tc_fence_after_sync();
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 0) {
+    // ================= TMA: this CTA's frame tile (hi, lo) and its half of the W3 block (hi, lo)
     uint32_t it = 0;
     for (int tile = tile_first, pit = (int)cluster_id_x(); pit < pair_iters; tile += tile_step, pit += (int)cluster_count_x()) {
       for (int kb = 0; kb < kHKBlocks; ++kb, ++it) {
-        const uint32_t s = it % kTStages, ph = (it / kTStages) & 1;
+        const uint32_t s = it % kHStages, ph = (it / kHStages) & 1;
         mbar_wait(&empty[s], ph ^ 1);
         if (elect_one()) {
-          uint8_t* st = smem + s * kTStageBytes;
-          mbar_arrive_expect_tx(&full[s], kTStageBytes);
+          uint8_t* st = smem + s * kHStageBytes;
+          mbar_arrive_expect_tx(&full[s], kHStageBytes);
           tma_load_2d(st, &map_ah, kb * kHK, tile * kTM, &full[s]);
-          tma_load_2d(st + kTABytes, &map_al, kb * kHK, tile * kTM, &full[s]);
-          // my half of the W3 block (128 of its 256 rows), to both CTAs
-          tma_load_2d_multicast(st + 2 * kTABytes + rank * (kTBBytes / 2), &map_bh, kb * kHK, (int)rank * 128, &full[s], 3);
-          tma_load_2d_multicast(st + 2 * kTABytes + kTBBytes + rank * (kTBBytes / 2), &map_bl, kb * kHK, (int)rank * 128, &full[s], 3);
+          tma_load_2d(st + kHTile, &map_al, kb * kHK, tile * kTM, &full[s]);
+          tma_load_2d(st + 2 * kHTile, &map_bh, kb * kHK, (int)rank * 128, &full[s]);
+          tma_load_2d(st + 3 * kHTile, &map_bl, kb * kHK, (int)rank * 128, &full[s]);
         }
         __syncwarp();
       }
     }
   } else if (warp == 1) {
-    const uint32_t idesc = make_idesc_f16(128, 256);
-    const uint32_t base = smem_u32(smem);
-    constexpr uint32_t hi = smem_desc_hi(1024, 2);
     uint32_t it = 0, run = 0, tcount = 0;
-    for (int tile = tile_first, pit = (int)cluster_id_x(); pit < pair_iters;
-         tile += tile_step, pit += (int)cluster_count_x(), ++tcount) {
-      mbar_wait(cross_empty, (tcount & 1) ^ 1);   // the previous tile's cross sums have been read
-      tc_fence_after_sync();
-      for (int r = 0; r < kHRuns; ++r, ++run) {
-        for (int kk = 0; kk < kHRunBlocks; ++kk, ++it) {
-          const uint32_t s = it % kTStages, ph = (it / kTStages) & 1;
-          mbar_wait(&full[s], ph);
-          tc_fence_after_sync();
-          const uint32_t st = base + s * kTStageBytes;
-          const uint32_t ah = smem_desc_lo(st, 16), al = smem_desc_lo(st + kTABytes, 16);
-          const uint32_t bh = smem_desc_lo(st + 2 * kTABytes, 16), bl = smem_desc_lo(st + 2 * kTABytes + kTBBytes, 16);
-          if (elect_one()) {
-#pragma unroll
-            for (int ks = 0; ks < kHK / 16; ++ks) {
-              const uint32_t o = (ks * 32) >> 4;
-              mma_f16_ss(tmem + 256, desc64(al + o, hi), desc64(bh + o, hi), idesc, (r | kk | ks) != 0);
-              mma_f16_ss(tmem + 256, desc64(ah + o, hi), desc64(bl + o, hi), idesc, 1);
-            }
-          }
-          __syncwarp();
-          if (kk == 0) {                          // the previous run has been folded: its accumulator may be restarted
-            mbar_wait(hh_empty, (run & 1) ^ 1);
+    if (rank == 0) {
+      // ================= MMA issuer (whole warp loops, one elected lane issues)
+      const uint32_t idesc = make_idesc_f16(256, 256);
+      const uint32_t base = smem_u32(smem);
+      constexpr uint32_t hi = smem_desc_hi(1024, 2);
+      for (int pit = (int)cluster_id_x(); pit < pair_iters; pit += (int)cluster_count_x(), ++tcount) {
+        mbar_wait(cross_empty, (tcount & 1) ^ 1);   // the previous tiles' cross sums have been read (both CTAs)
+        tc_fence_after_sync();
+        for (int r = 0; r < kHRuns; ++r, ++run) {
+          for (int kk = 0; kk < kHRunBlocks; ++kk, ++it) {
+            const uint32_t s = it % kHStages, ph = (it / kHStages) & 1;
+            mbar_wait(&full[s], ph);                // own TMA and the peer's relay
             tc_fence_after_sync();
-          }
-          if (elect_one()) {
+            const uint32_t st = base + s * kHStageBytes;
+            const uint32_t ah = smem_desc_lo(st, 16), al = smem_desc_lo(st + kHTile, 16);
+            const uint32_t bh = smem_desc_lo(st + 2 * kHTile, 16), bl = smem_desc_lo(st + 3 * kHTile, 16);
+            if (elect_one()) {
 #pragma unroll
-            for (int ks = 0; ks < kHK / 16; ++ks) {
-              const uint32_t o = (ks * 32) >> 4;
-              mma_f16_ss(tmem, desc64(ah + o, hi), desc64(bh + o, hi), idesc, (kk | ks) != 0);
+              for (int ks = 0; ks < kHK / 16; ++ks) {
+                const uint32_t o = (ks * 32) >> 4;
+                mma_f16_ss_pair(tmem + 256, desc64(al + o, hi), desc64(bh + o, hi), idesc, (r | kk | ks) != 0);
+                mma_f16_ss_pair(tmem + 256, desc64(ah + o, hi), desc64(bl + o, hi), idesc, 1);
+              }
             }
-            mma_commit_multicast(&empty[s], 3);
-            if (kk == kHRunBlocks - 1) mma_commit(hh_full);
+            __syncwarp();
+            if (kk == 0) {                          // the previous run has been folded: its accumulator may be restarted
+              mbar_wait(hh_empty, (run & 1) ^ 1);
+              tc_fence_after_sync();
+            }
+            if (elect_one()) {
+#pragma unroll
+              for (int ks = 0; ks < kHK / 16; ++ks) {
+                const uint32_t o = (ks * 32) >> 4;
+                mma_f16_ss_pair(tmem, desc64(ah + o, hi), desc64(bh + o, hi), idesc, (kk | ks) != 0);
+              }
+              mma_commit_pair(&empty[s]);
+              if (kk == kHRunBlocks - 1) mma_commit_pair(hh_full);
+            }
+            __syncwarp();
           }
+        }
+      }
+    } else {
+      // ================= relay (peer CTA): forwards "my stage is full" to the leader's barrier
+      for (int pit = (int)cluster_id_x(); pit < pair_iters; pit += (int)cluster_count_x()) {
+        for (int kb = 0; kb < kHKBlocks; ++kb, ++it) {
+          const uint32_t s = it % kHStages, ph = (it / kHStages) & 1;
+          mbar_wait(&full[s], ph);
+          if (elect_one()) mbar_arrive_remote(&full[s], 0);
           __syncwarp();
         }
       }
     }
   } else {
+    // ================= epilogue: fold the hi*hi runs into fp32 master sums, add the cross sums, +b3, ReLU -> h
     const int q = warp & 3, half = (warp - 2) >> 2;          // TMEM lane quarter, column half
-    const float* b3s = reinterpret_cast<const float*>(smem + DenseT32Smem::b3) + half * 128;
+    const float* b3s = reinterpret_cast<const float*>(smem + DenseF16Smem::b3) + half * 128;
     uint32_t run = 0;
+    auto release = [&](uint64_t* bar) {           // one arrival per epilogue warp on the LEADER's barrier
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) {
+        if (rank == 0) mbar_arrive(bar);
+        else mbar_arrive_remote(bar, 0);
+      }
+    };
     for (int tile = tile_first, pit = (int)cluster_id_x(); pit < pair_iters; tile += tile_step, pit += (int)cluster_count_x()) {
       float acc[128];
 #pragma unroll
@@ -1162,9 +1202,7 @@ vt_dense_f16x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_c
             acc[g * 32 + 32 + e] += __uint_as_float(v1[e]);
           }
         }
-        tc_fence_before_sync();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(hh_empty);
+        release(hh_empty);
       }
       // the last run's commit also covers every cross MMA of the tile
 #pragma unroll
@@ -1179,9 +1217,7 @@ vt_dense_f16x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_c
           acc[g * 32 + 32 + e] = fmaf(__uint_as_float(v1[e]), 1.f / 2048.f, acc[g * 32 + 32 + e]);
         }
       }
-      tc_fence_before_sync();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(cross_empty);
+      release(cross_empty);
       const long long row = (long long)tile * kTM + q * 32 + lane;
       if (row < n) {
         float* dst = hbuf + row * 256 + half * 128;
@@ -1198,13 +1234,13 @@ vt_dense_f16x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_c
     }
   }
 
+  // ---- teardown (the pair leaves together: the leader's MMAs read the peer's shared memory)
   __syncwarp();
   tc_fence_before_sync();
   __syncthreads();
-  cluster_sync_all();                            // no multicast may target a CTA that has already exited
-  if (warp == 0) tmem_dealloc<512>(tmem);
+  cluster_sync_all();
+  if (warp == 0) tmem_dealloc_pair<512>(tmem);
 }
-
 
 // ------------------------------------------------------------------------------------------
 // host side
@@ -1386,7 +1422,7 @@ int pack_vt_bf16(mdc_handle_s* h) {      // the tensor-core modes (MDC_MODE_BF16
   MDC_CUDA(cudaFuncSetAttribute(vt_conv_kernel<kConvTF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<kConvTF32>::total));
   MDC_CUDA(cudaFuncSetAttribute(vt_conv_kernel<kConvF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<kConvF16>::total));
   MDC_CUDA(cudaFuncSetAttribute(vt_dense_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DenseT32Smem::total));
-  MDC_CUDA(cudaFuncSetAttribute(vt_dense_f16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DenseT32Smem::total));
+  MDC_CUDA(cudaFuncSetAttribute(vt_dense_f16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DenseF16Smem::total));
   if (cm == kConvBF16) {
     switch (h->C) {
 #define MDC_DENSE_ATTR(CC) \
@@ -1514,7 +1550,7 @@ int launch_vt_dense_head(mdc_handle_s* h, int64_t m, float* probs, float* dense,
     const uint16_t* act = reinterpret_cast<const uint16_t*>(h->ws_act.ptr);
     if (int e = make_kmajor_map(&map_ah, act, (uint64_t)m, kElemF16, kTM)) return e;
     if (int e = make_kmajor_map(&map_al, act + h->vt_act_elems, (uint64_t)m, kElemF16, kTM)) return e;
-    vt_dense_f16x3_kernel<<<grid_d, kDenseT32Threads, DenseT32Smem::total, stream>>>(map_ah, map_al, wmaps[0], wmaps[1],
+    vt_dense_f16x3_kernel<<<grid_d, kDenseT32Threads, DenseF16Smem::total, stream>>>(map_ah, map_al, wmaps[0], wmaps[1],
                                                                                       b3, hb, m, tiles);
   } else {
     const float* act = reinterpret_cast<const float*>(h->ws_act.ptr);
