@@ -449,10 +449,11 @@ def run_ours(args):
             okms, okl, okname = mo._h.profile_read()
             modes[other] = {"value": batch * k_steps / (mms * 1e-3), "unit": UNIT, "ms_per_step": mms / k_steps, "steps": k_steps}
             if other in MODE_COST and okl:
-                o_ach = VT_CONV_FLOP_PER_FRAME * batch / (okms / okl * 1e-3) / 1e12
+                # (tf32x3 runs passes of 18,944 frames: several conv launches per step)
+                o_ach = VT_CONV_FLOP_PER_FRAME * batch * k_steps / (okms * 1e-3) / 1e12
                 o_peak = peaks["bf16_tflops"] / MODE_COST[other]
                 modes[other]["roofline"] = {"kernel": okname, "achieved": o_ach, "peak": o_peak, "unit": "TFLOP/s",
-                                            "frac": o_ach / o_peak, "avg_launch_ms": okms / okl,
+                                            "frac": o_ach / o_peak, "avg_launch_ms": okms / okl, "launches_per_step": okl / k_steps,
                                             "traffic": NCU_TRAFFIC.get(other, (None, None))[0]}
             mo.close()
         for k in modes:

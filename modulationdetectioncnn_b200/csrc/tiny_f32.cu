@@ -323,6 +323,211 @@ tiny_f32_kernel(const TinyParams p, const float4* __restrict__ dmain, const floa
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Second formulation (default for the shipped shapes, F in {3, 10}, C <= 4): FOUR frames per warp pass.
+//
+// What the counters of the kernel above say (ncu, F = 10: 483 warp-instructions per frame against ~283 of useful
+// math, issue slots 64 % busy, 131 shared-memory wavefronts per frame): every lane needs its own 2 F C float4 of Dense
+// weights, so a warp pass streams the WHOLE 30 KB weight image through the LSU - 240 cycles per pass, 120 per frame at
+// two frames per pass, more than the 100 cycles per frame the FMA pipe needs; and the conv constants are packed into
+// register pairs with MOVs on every pass.  Here a pass covers four frames (60 wavefronts per frame), the conv
+// constants arrive pre-duplicated as 64-bit kernel parameters (FFMA2 reads them straight from the constant bank),
+// and the frames come through a per-warp ring of three 4 KB buffers filled by 1-D bulk copies (one elected lane, one
+// mbarrier per buffer, no register prefetch, no coupling between warps: a warp refills the buffer it has just read).
+struct TinyParams4 {
+  unsigned long long k0[kMaxFilters], k1[kMaxFilters], b[kMaxFilters];   // {v, v} pairs
+  float bias[kMaxClasses];
+  float zero;                                                            // 0.0f (see the shifted pairs in the kernel)
+};
+
+template <int F, int C, int W, int B>
+struct Tiny4 {
+  static constexpr int kWarps = W, kThreads = kWarps * 32, R = 4, kBufs = B;
+  static constexpr int kWBytes = 2 * F * C * 128 * 4;
+  static constexpr int ring = kWBytes;
+  static constexpr int bars = ring + kWarps * kBufs * R * 1024;
+  static constexpr int total = bars + kWarps * kBufs * 8;
+  static_assert(C <= 4 && 2 * F <= 32, "shape outside the specialisation");
+};
+
+template <int F, int C, int W, int B>
+__global__ void __launch_bounds__(Tiny4<F, C, W, B>::kThreads, 1)
+tiny_f32_kernel4(const __grid_constant__ TinyParams4 p, const float4* __restrict__ dmain, const float* __restrict__ dtail,
+                 const float* __restrict__ x, long long n, float* __restrict__ probs, float* __restrict__ dense,
+                 int* __restrict__ cls, unsigned long long* __restrict__ hist) {
+  using Cfg = Tiny4<F, C, W, B>;
+  constexpr int R = Cfg::R, kBufs = Cfg::kBufs;
+  extern __shared__ __align__(128) uint8_t smem[];
+  const float4* wsm = reinterpret_cast<const float4*>(smem);
+  const int lane = threadIdx.x & 31, warp = uniform_warp_idx();
+  uint8_t* myring = smem + Cfg::ring + warp * (kBufs * R * 1024);
+  uint64_t* mybar = reinterpret_cast<uint64_t*>(smem + Cfg::bars) + warp * kBufs;
+
+  {
+    float4* wdst = reinterpret_cast<float4*>(smem);
+    for (int i = threadIdx.x; i < 2 * F * C * 32; i += Cfg::kThreads) wdst[i] = __ldg(dmain + i);
+  }
+  if (lane == 0) {
+    for (int b = 0; b < kBufs; ++b) mbar_init(&mybar[b], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+
+  // position 128: lane j < 2F handles (r = j / F, f = j % F)
+  float tw[C];
+  float tk0 = 0.f, tb = 0.f;
+  const int tr = lane / F;
+#pragma unroll
+  for (int c = 0; c < C; ++c) tw[c] = 0.f;
+  if (lane < 2 * F) {
+    const int tf = lane % F;
+    tk0 = __uint_as_float((unsigned)(p.k0[tf] & 0xFFFFFFFFull));
+    tb = __uint_as_float((unsigned)(p.b[tf] & 0xFFFFFFFFull));
+#pragma unroll
+    for (int c = 0; c < C; ++c) tw[c] = __ldg(dtail + (tr * F + tf) * C + c);
+  }
+
+  // groups of R consecutive frames, dealt round-robin to the warps of the grid
+  const long long ngroups = (n + R - 1) / R;
+  const long long stride = (long long)gridDim.x * Cfg::kWarps;
+  long long g = (long long)blockIdx.x * Cfg::kWarps + warp;
+  auto issue = [&](long long grp, int b) {        // this warp's frames of group grp -> buffer b
+    if (grp < ngroups && elect_one()) {
+      const long long f0 = grp * R, left = n - f0;
+      const uint32_t bytes = (uint32_t)(left < R ? left : R) * 1024u;
+      mbar_arrive_expect_tx(&mybar[b], bytes);
+      bulk_g2s(myring + b * (R * 1024), x + f0 * 256, bytes, &mybar[b]);
+    }
+    __syncwarp();
+  };
+  // kBufs - 1 passes in flight
+  issue(g, 0);
+  if (kBufs > 2) issue(g + stride, 1);
+  unsigned cnt = 0;
+  for (uint32_t it = 0; g < ngroups; g += stride, ++it) {
+    const uint32_t b = it % kBufs;
+    // the buffer read in the previous pass is free: every value loaded from it has been consumed by then
+    issue(g + (kBufs - 1) * stride, (it + kBufs - 1) % kBufs);
+    mbar_wait(&mybar[b], (it / kBufs) & 1);
+    const float* fr = reinterpret_cast<const float*>(myring + b * (R * 1024));
+    const long long f0 = g * R;
+
+    uint64_t acc[R][C];       // {even positions, odd positions} partial sums
+    uint64_t PI01[R], PI23[R], XI01[R], XI23[R], PQ01[R], PQ23[R], XQ01[R], XQ23[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const float4 xi = reinterpret_cast<const float4*>(fr + r * 256)[lane];
+      const float4 xq = reinterpret_cast<const float4*>(fr + r * 256 + 128)[lane];
+      const float pi = lane ? fr[r * 256 + 4 * lane - 1] : 0.f;
+      const float pq = lane ? fr[r * 256 + 128 + 4 * lane - 1] : 0.f;
+      // y[i] = relu(x[i-1] k0 + x[i] k1 + b): pairs (y0,y1) and (y2,y3)
+      // The shifted pairs (x[4l-1], x[4l]) and (x[4l+1], x[4l+2]) straddle the register pairs the 16-B loads fill.
+      // Built with plain moves, ptxas re-copies them next to every use (170 MOVs per pass for F = 10); an add of a
+      // zero it cannot see through (a kernel parameter) gives each shifted pair registers of its own, once per pass.
+      PI01[r] = f2_pack(pi, xi.x + p.zero);           PI23[r] = f2_pack(xi.y + p.zero, xi.z + p.zero);
+      XI01[r] = f2_pack(xi.x, xi.y);                  XI23[r] = f2_pack(xi.z, xi.w);
+      PQ01[r] = f2_pack(pq, xq.x + p.zero);           PQ23[r] = f2_pack(xq.y + p.zero, xq.z + p.zero);
+      XQ01[r] = f2_pack(xq.x, xq.y);                  XQ23[r] = f2_pack(xq.z, xq.w);
+#pragma unroll
+      for (int c = 0; c < C; ++c) acc[r][c] = 0ull;
+    }
+#pragma unroll
+    for (int k = 0; k < F; ++k) {
+      float4 wi[C], wq[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        wi[c] = wsm[((0 * F + k) * C + c) * 32 + lane];
+        wq[c] = wsm[((1 * F + k) * C + c) * 32 + lane];
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const uint64_t yi01 = f2_relu(f2_fma(p.k0[k], PI01[r], f2_fma(p.k1[k], XI01[r], p.b[k])));
+        const uint64_t yi23 = f2_relu(f2_fma(p.k0[k], PI23[r], f2_fma(p.k1[k], XI23[r], p.b[k])));
+        const uint64_t yq01 = f2_relu(f2_fma(p.k0[k], PQ01[r], f2_fma(p.k1[k], XQ01[r], p.b[k])));
+        const uint64_t yq23 = f2_relu(f2_fma(p.k0[k], PQ23[r], f2_fma(p.k1[k], XQ23[r], p.b[k])));
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          uint64_t a = acc[r][c];
+          a = f2_fma(yi01, f2_pack(wi[c].x, wi[c].y), a);
+          a = f2_fma(yi23, f2_pack(wi[c].z, wi[c].w), a);
+          a = f2_fma(yq01, f2_pack(wq[c].x, wq[c].y), a);
+          a = f2_fma(yq23, f2_pack(wq[c].z, wq[c].w), a);
+          acc[r][c] = a;
+        }
+      }
+    }
+    // Cross-lane sums of the 4 x 4 (frame, class) partials by recursive halving: every step halves the values a lane
+    // carries (8 + 4 + 2 + 1 + 1 shuffles instead of 5 per value) and leaves the sum for (frame r, class c) in the
+    // lanes with bits 4..3 = r, bits 2..1 = c.
+    float v[16];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (c < C) {
+          float lo, hi;
+          f2_unpack(acc[r][c], lo, hi);
+          v[r * 4 + c] = lo + hi;
+        } else {
+          v[r * 4 + c] = 0.f;
+        }
+      }
+    // position 128: xp[128] = x[127], xp[129] = 0 (the frames are still in this pass's buffer)
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const float yt = fmaxf(fmaf(fr[r * 256 + (lane < 2 * F ? tr : 0) * 128 + 127], tk0, tb), 0.f);
+#pragma unroll
+      for (int c = 0; c < C; ++c) v[r * 4 + c] = fmaf(yt, tw[c], v[r * 4 + c]);   // tw = 0 in lanes without a (row, filter)
+    }
+    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
+    float w8[8], w4[4], w2[2];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) w8[j] = (b4 ? v[8 + j] : v[j]) + __shfl_xor_sync(0xffffffffu, b4 ? v[j] : v[8 + j], 16);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) w4[j] = (b3 ? w8[4 + j] : w8[j]) + __shfl_xor_sync(0xffffffffu, b3 ? w8[j] : w8[4 + j], 8);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) w2[j] = (b2 ? w4[2 + j] : w4[j]) + __shfl_xor_sync(0xffffffffu, b2 ? w4[j] : w4[2 + j], 4);
+    float t = (b1 ? w2[1] : w2[0]) + __shfl_xor_sync(0xffffffffu, b1 ? w2[0] : w2[1], 2);
+    t += __shfl_xor_sync(0xffffffffu, t, 1);
+    const int myc = (lane >> 1) & 3, grp8 = lane & 24;
+    float bsel = p.bias[0];
+#pragma unroll
+    for (int c = 1; c < C; ++c) if (myc == c) bsel = p.bias[c];
+    t = fmaxf(t + bsel, 0.f);
+    float z[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) z[c] = __shfl_sync(0xffffffffu, t, grp8 + 2 * c);
+    const long long f = f0 + (lane >> 3);
+    if (f < n) {
+      int best = 0;
+      float m = z[0];
+#pragma unroll
+      for (int c = 1; c < C; ++c) if (z[c] > m) { m = z[c]; best = c; }
+      float e[C], sum = 0.f;
+#pragma unroll
+      for (int c = 0; c < C; ++c) { e[c] = expf(z[c] - m); sum += e[c]; }
+      const float inv = 1.0f / sum;
+      const int l8 = lane & 7;                   // lane c of each 8-lane group writes class c of its frame
+      float zsel = z[0], psel = e[0] * inv;
+#pragma unroll
+      for (int c = 1; c < C; ++c) if (l8 == c) { zsel = z[c]; psel = e[c] * inv; }
+      if (l8 < C) {
+        if (dense) dense[f * C + l8] = zsel;
+        if (probs) probs[f * C + l8] = psel;
+      }
+      if (l8 == 0 && cls) cls[f] = best;
+      cnt += (l8 == best);
+    }
+    __syncwarp();                                // every lane has read this pass's buffer before it is refilled
+  }
+  if (hist) {
+    // lanes 8 j + c counted class c for the frames j of this warp's passes
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, 8);
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, 16);
+    if (lane < C && cnt) atomicAdd(hist + lane, (unsigned long long)cnt);
+  }
+}
+
 __device__ __forceinline__ float4 ldg_stream_f4(const float4* p) {
   float4 r;
   asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
@@ -450,14 +655,15 @@ int launch_tiny_f32(mdc_handle_s* h, const float* x, int64_t n, float* probs, fl
     return (unsigned)(blocks > max_blocks ? max_blocks : blocks);
   };
   // variant selection (MDC_TINY_VARIANT, tuning aid).  Measured on B200, 2^21 frames, frames/s:
-  //   3 (default) direct loads, no ring, 8 consumer warps, 2 CTAs/SM     F=3: 3.42e9   F=10: 1.51e9
+  //   3           direct loads, no ring, 8 consumer warps, 2 CTAs/SM     F=3: 3.42e9   F=10: 1.51e9
   //   2           direct loads, 3 CTAs/SM (80 registers, small spills)   F=3: 3.39e9   F=10: 1.45e9
   //   1           TMA ring, Dense rows in shared memory, 3 CTAs/SM       F=3: 3.14e9   F=10: 1.32e9
   //   0           TMA ring, Dense rows in registers (F=3) / 2 CTAs/SM    F=3: 2.55e9   F=10: 1.21e9
   // The ring keeps more bytes in flight, but these kernels are issue-bound, not latency-bound, and the ring couples
   // the consumer warps of a CTA (a stage is refilled only when the slowest of seven warps has taken its frames:
   // 15 % of the consumers' samples sat in the full-barrier wait) and spends a warp on the producer.
-  static const int variant = getenv("MDC_TINY_VARIANT") ? atoi(getenv("MDC_TINY_VARIANT")) : 3;
+  //   4 (default) tiny_f32_kernel4: four frames per warp pass, per-warp bulk-copy ring, 14 warps, 1 CTA/SM
+  static const int variant = getenv("MDC_TINY_VARIANT") ? atoi(getenv("MDC_TINY_VARIANT")) : 4;
   auto ring_grid = [&](int R, int ctas_per_sm, int cons = kTinyConsumers) {
     const long long nblocks = (n + cons * R - 1) / (cons * R);
     const long long max_blocks = (long long)h->num_sms * ctas_per_sm;
@@ -476,8 +682,40 @@ int launch_tiny_f32(mdc_handle_s* h, const float* x, int64_t n, float* probs, fl
                                                     kTinyThreads, smem_, stream>>>(                         \
         p, dm, dt, x, n, probs, dense, cls, hist);                                                          \
   } while (0)
+#define MDC_TINY4_LAUNCH(F_, C_, W_, B_)                                                                      \
+  do {                                                                                                        \
+    using Cfg_ = Tiny4<F_, C_, W_, B_>;                                                                       \
+    static bool attr_ = false;                                                                                \
+    if (!attr_) {                                                                                             \
+      MDC_CUDA(cudaFuncSetAttribute(tiny_f32_kernel4<F_, C_, W_, B_>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg_::total)); \
+      attr_ = true;                                                                                           \
+    }                                                                                                         \
+    const long long ngroups_ = (n + Cfg_::R - 1) / Cfg_::R;                                                   \
+    const long long blocks_ = (ngroups_ + Cfg_::kWarps - 1) / Cfg_::kWarps;                                   \
+    const unsigned grid_ = (unsigned)(blocks_ < h->num_sms ? blocks_ : h->num_sms);                           \
+    tiny_f32_kernel4<F_, C_, W_, B_><<<grid_, Cfg_::kThreads, Cfg_::total, stream>>>(p4, dm, dt, x, n, probs, dense, cls, hist); \
+  } while (0)
+  TinyParams4 p4;
+  for (int f = 0; f < kMaxFilters; ++f) {
+    auto dup = [](float v) {
+      unsigned u;
+      memcpy(&u, &v, 4);
+      return ((unsigned long long)u << 32) | u;
+    };
+    p4.k0[f] = dup(p.conv[3 * f]);
+    p4.k1[f] = dup(p.conv[3 * f + 1]);
+    p4.b[f] = dup(p.conv[3 * f + 2]);
+  }
+  for (int c = 0; c < kMaxClasses; ++c) p4.bias[c] = p.bias[c];
+  p4.zero = 0.f;
   prof_begin(h, stream);
-  if (F == 3 && C == 3) {
+  // 16 warps x 3 buffers: measured against 14 warps (F = 10: 1.60e9 -> 1.84e9 frames/s - the kernel wants warps to
+  // fill the FMA pipe's off-cycles); 18+ warps would leave < 128 registers per thread and spill
+  if (F == 3 && C == 3 && variant >= 4) {
+    MDC_TINY4_LAUNCH(3, 3, 16, 3);
+  } else if (F == 10 && C == 3 && variant >= 4) {
+    MDC_TINY4_LAUNCH(10, 3, 16, 3);
+  } else if (F == 3 && C == 3) {
     if (variant == 3) MDC_TINY_LAUNCH(3, 3, 2, 0, false, 2);
     else if (variant == 2) MDC_TINY_LAUNCH(3, 3, 2, 0, false, 3);
     else if (variant == 1) MDC_TINY_LAUNCH(3, 3, 2, 4, false, 3);

@@ -90,3 +90,29 @@ def test_reads_reference_h5_when_present(reference_dir, h5w):
     assert (m.kind, m.filters, m.classes) == ("tiny", 3, 3)
     x = philox(1).normal(0, 2 ** -7, (64, 2, 128)).astype(np.float32)
     assert np.array_equal(m.predict(x), _model(h5w["A_3conv"]).predict(x))
+
+
+@pytest.mark.parametrize("tag", ["A_3conv", "E_f10"])
+def test_large_batch_wraps_the_frame_ring(h5w, tag):
+    """2^19 + 5 frames: every warp of the 148 x 14 grid runs ~63 four-frame passes, so its three-buffer bulk-copy ring
+    wraps ~21 times, the mbarrier phases flip, and the last pass is ragged (one frame).  The batch is a 4,099-frame block
+    repeated: every copy must give the bits of the first, which is checked against the fp64 oracle; plus ragged sizes
+    around the pass width, and the class histogram (one atomic per class and warp)."""
+    import torch
+    from oracle import cnn2_float as cf
+    w = h5w[tag]
+    base = philox(2016).normal(0, 2 ** -7, (4099, 2, 128)).astype(np.float32)
+    base[:3] *= 300
+    n = (1 << 19) + 5
+    x = torch.from_numpy(np.tile(base, (n // 4099 + 1, 1, 1))[:n].copy()).cuda()
+    m = _model(w)
+    z = m.predict(x, output="dense").cpu().numpy()
+    np.testing.assert_allclose(z[:4099], cf.tiny_cnn2_forward(base, *w, output="dense"), rtol=RTOL, atol=1e-6)
+    full = n // 4099
+    assert np.array_equal(z[:full * 4099].reshape(full, 4099, 3), np.broadcast_to(z[:4099], (full, 4099, 3)))
+    assert np.array_equal(z[full * 4099:], z[:n - full * 4099])
+    cls = m.predict_classes(x).cpu().numpy()
+    assert np.array_equal(cls, z.argmax(-1))
+    assert m.class_histogram(x).cpu().numpy().tolist() == np.bincount(cls, minlength=3).tolist()
+    for k in (1, 2, 3, 4, 5, 7, 57):
+        assert np.array_equal(m.predict(x[:k], output="dense").cpu().numpy(), z[:k]), k
