@@ -9,11 +9,17 @@
 //
 // Mapping: one warp per frame.  Lane l owns sample positions s = 4l..4l+3 of both rows, so
 // a frame is two fully coalesced 512 B int4 loads per warp.  The dense ROM entries a lane
-// needs never change (they depend only on s), so for the shipped F=3,C=3 geometry they
-// live in 72 registers for the whole (persistent) kernel; the conv table and biases sit
-// in kernel-parameter constant memory.  Class sums are reduced with REDUX
+// needs depend only on s; they are re-read through L1 (one LDG.128 per 4 entries, the
+// 9-30 KB image stays L1-resident) so that a thread needs 64 registers and eight warps
+// per scheduler are resident: the kernel is bound by instruction issue (about 315 warp
+// instructions per frame, 204 of them the MACs, shifts and max of the arithmetic itself),
+// and more resident warps - not fewer instructions or ROM rows kept in registers - are
+// what raised the issue rate (measured, profiles/r02_q612.md).  The conv table and biases
+// sit in kernel-parameter constant memory.  Class sums are reduced with REDUX
 // (__reduce_add_sync): 32-bit wrap-around addition is associative, so the reduction order
 // cannot change the result.
+#include <algorithm>
+
 #include "mdc_internal.cuh"
 
 namespace mdc {
@@ -72,10 +78,18 @@ __device__ __forceinline__ int conv18_sel(int a, int w0, int c, int w1, int bias
   return o < 0 ? 0 : o;
 }
 
+// ROM rows are re-read through L1 for every frame; volatile so that the compiler does not hoist these
+// (loop-invariant) loads out of the frame loop and spill them
+__device__ __forceinline__ int4 ldg_rom(const int4* p) {
+  int4 r;
+  asm volatile("ld.global.nc.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+
 // class sums of one frame (lane = 4 sample positions of both rows)
-template <int F, int C, bool WREG, bool FAST>
-__device__ __forceinline__ void frame_sums(const QParams& p, const int4* __restrict__ dense4, const int4 (&w)[WREG ? F * C * 2 : 1],
-                                           const int (&I)[5], const int (&Q)[5], int lane, unsigned (&acc)[C]) {
+template <int F, int C, bool FAST>
+__device__ __forceinline__ void frame_sums(const QParams& p, const int4* __restrict__ dense4, const int (&I)[5],
+                                           const int (&Q)[5], int lane, unsigned (&acc)[C]) {
 #pragma unroll
   for (int c = 0; c < C; ++c) acc[c] = 0u;
 #pragma unroll
@@ -89,14 +103,8 @@ __device__ __forceinline__ void frame_sums(const QParams& p, const int4* __restr
     }
 #pragma unroll
     for (int c = 0; c < C; ++c) {
-      int4 wi, wq;
-      if (WREG) {
-        wi = w[(k * C + c) * 2];
-        wq = w[(k * C + c) * 2 + 1];
-      } else {
-        wi = __ldg(dense4 + ((k * C + c) * 2) * 32 + lane);
-        wq = __ldg(dense4 + ((k * C + c) * 2 + 1) * 32 + lane);
-      }
+      const int4 wi = ldg_rom(dense4 + ((k * C + c) * 2) * 32 + lane);
+      const int4 wq = ldg_rom(dense4 + ((k * C + c) * 2 + 1) * 32 + lane);
       acc[c] += (unsigned)slice_sel<FAST>(yi[0], wi.x, yq[0], wq.x) + (unsigned)slice_sel<FAST>(yi[1], wi.y, yq[1], wq.y) +
                 (unsigned)slice_sel<FAST>(yi[2], wi.z, yq[2], wq.z) + (unsigned)slice_sel<FAST>(yi[3], wi.w, yq[3], wq.w);
     }
@@ -110,66 +118,71 @@ __device__ __forceinline__ int4 ldg_stream(const int4* p) {
   return r;
 }
 
+// One frame of the persistent loop.  The range test runs on the RAW words: when every |x| is below the small-signal
+// bound the 18-bit wrap is the identity and is skipped; any other frame is wrapped and takes the 36-bit slices.
+// Lane c ends up with class c's sum, so each output array costs one predicated store per frame.
+//   wmask: bit 0 = this lane stores `out`, bit 1 = `pre`, bit 2 = `cls` (set up once per kernel)
+template <int F, int C>
+__device__ __forceinline__ void q612_frame(const QParams& p, const int4* __restrict__ dense4,
+                                           const int4& xi, const int4& xq, int lane, unsigned f, unsigned wmask,
+                                           int* __restrict__ out, int* __restrict__ pre, int* __restrict__ cls, unsigned& cnt) {
+  int I[5] = {0, xi.x, xi.y, xi.z, xi.w}, Q[5] = {0, xq.x, xq.y, xq.z, xq.w};
+  I[0] = __shfl_up_sync(0xffffffffu, I[4], 1);
+  Q[0] = __shfl_up_sync(0xffffffffu, Q[4], 1);
+  if (lane == 0) { I[0] = 0; Q[0] = 0; }   // zero padding: ad_in_data[0] (sv:485)
+  const int hi = max(max(max(I[1], I[2]), max(I[3], I[4])), max(max(Q[1], Q[2]), max(Q[3], Q[4])));
+  const int lo = min(min(min(I[1], I[2]), min(I[3], I[4])), min(min(Q[1], Q[2]), min(Q[3], Q[4])));
+  const int xmax = __reduce_max_sync(0xffffffffu, max(hi, ~lo));   // < X  =>  -X <= x < X for every sample
+  unsigned acc[C];   // unsigned: wrap-around mod 2^32 is defined behaviour
+  if (xmax < p.xfast) {
+    frame_sums<F, C, true>(p, dense4, I, Q, lane, acc);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 5; ++i) { I[i] = wrap18(I[i]); Q[i] = wrap18(Q[i]); }
+    frame_sums<F, C, false>(p, dense4, I, Q, lane, acc);
+  }
+  int mine = 0, best = 0, bestv = 0;
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    const int s = (int)(__reduce_add_sync(0xffffffffu, acc[c]) + (unsigned)p.bias[c]);
+    const int o = s < 0 ? 0 : s;
+    if (lane == c) mine = s;
+    if (c == 0 || o > bestv) { bestv = o; best = c; }
+  }
+  const unsigned at = f * (unsigned)C + (unsigned)lane;
+  if (wmask & 2u) pre[at] = mine;
+  if (wmask & 1u) out[at] = mine < 0 ? 0 : mine;
+  if (wmask & 4u) cls[f] = best;
+  cnt += (lane == best);
+}
+
 // dense image: [f][c][iq][128] with entry s = tab[2c+iq][128 f + max(s-1,0)]  (pre-skewed on host)
-template <int F, int C, bool WREG, int MINB>
+// n * C < 2^32 (launch_q612 splits longer batches): frame and output indices are 32-bit.
+template <int F, int C, int MINB>
 __global__ void __launch_bounds__(256, MINB)
 q612_kernel(const QParams p, const int4* __restrict__ dense4, const int4* __restrict__ x,
-            long long n, int* __restrict__ out, int* __restrict__ pre, int* __restrict__ cls,
+            unsigned n, int* __restrict__ out, int* __restrict__ pre, int* __restrict__ cls,
             unsigned long long* __restrict__ hist) {
   const int lane = threadIdx.x & 31;
-  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-
-  int4 w[WREG ? F * C * 2 : 1];
-  if (WREG) {
-#pragma unroll
-    for (int i = 0; i < F * C * 2; ++i) w[i] = __ldg(dense4 + i * 32 + lane);
-  }
+  const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned nwarps = (gridDim.x * blockDim.x) >> 5;
+  const unsigned wmask = (out && lane < C ? 1u : 0u) | (pre && lane < C ? 2u : 0u) | (cls && lane == 0 ? 4u : 0u);
   unsigned cnt = 0;
 
-  long long f = warp;
+  unsigned f = warp;
   int4 xi, xq;
   if (f < n) {
-    xi = ldg_stream(x + f * 64 + lane);
-    xq = ldg_stream(x + f * 64 + 32 + lane);
+    xi = ldg_stream(x + (size_t)f * 64 + lane);
+    xq = ldg_stream(x + (size_t)f * 64 + 32 + lane);
   }
   while (f < n) {
-    const long long fn = f + nwarps;
+    const unsigned fn = f + nwarps;
     int4 ni = xi, nq = xq;
-    if (fn < n) {  // prefetch the next frame of this warp (a second frame in flight measured slower: the kernel is
-                   // issue-bound, not latency-bound)
-      ni = ldg_stream(x + fn * 64 + lane);
-      nq = ldg_stream(x + fn * 64 + 32 + lane);
+    if (fn < n) {  // prefetch the next frame of this warp
+      ni = ldg_stream(x + (size_t)fn * 64 + lane);
+      nq = ldg_stream(x + (size_t)fn * 64 + 32 + lane);
     }
-    int I[5], Q[5];
-    I[1] = wrap18(xi.x); I[2] = wrap18(xi.y); I[3] = wrap18(xi.z); I[4] = wrap18(xi.w);
-    Q[1] = wrap18(xq.x); Q[2] = wrap18(xq.y); Q[3] = wrap18(xq.z); Q[4] = wrap18(xq.w);
-    I[0] = __shfl_up_sync(0xffffffffu, I[4], 1);
-    Q[0] = __shfl_up_sync(0xffffffffu, Q[4], 1);
-    if (lane == 0) { I[0] = 0; Q[0] = 0; }   // zero padding: ad_in_data[0] (sv:485)
-
-    unsigned acc[C];   // unsigned: wrap-around mod 2^32 is defined behaviour
-    {
-      // largest |x| of the frame decides (warp-uniformly) between the 32-bit and the 36-bit arithmetic
-      int ax = max(max(abs(I[1]), abs(I[2])), max(abs(I[3]), abs(I[4])));
-      ax = max(ax, max(max(abs(Q[1]), abs(Q[2])), max(abs(Q[3]), abs(Q[4]))));
-      const int xmax = __reduce_max_sync(0xffffffffu, ax);
-      if (xmax <= p.xfast) frame_sums<F, C, WREG, true>(p, dense4, w, I, Q, lane, acc);
-      else frame_sums<F, C, WREG, false>(p, dense4, w, I, Q, lane, acc);
-    }
-    int best = 0, bestv = 0;
-#pragma unroll
-    for (int c = 0; c < C; ++c) {
-      int s = (int)(__reduce_add_sync(0xffffffffu, acc[c]) + (unsigned)p.bias[c]);
-      int o = s < 0 ? 0 : s;
-      if (lane == 0) {
-        if (pre) pre[f * C + c] = s;
-        if (out) out[f * C + c] = o;
-      }
-      if (c == 0 || o > bestv) { bestv = o; best = c; }
-    }
-    if (lane == 0 && cls) cls[f] = best;
-    cnt += (lane == best);
+    q612_frame<F, C>(p, dense4, xi, xq, lane, f, wmask, out, pre, cls, cnt);
     xi = ni; xq = nq;
     f = fn;
   }
@@ -248,22 +261,26 @@ int launch_q612(mdc_handle_s* h, const int32_t* x, int64_t n, int32_t* out, int3
   p.xfast = h->q_xfast;
   const int threads = 256;
   long long warps_needed = n;
-  // MDC_Q612_VARIANT (tuning aid): 0 = ROM rows in registers, 2 CTAs/SM; 1 = ROM rows through L1, 4 CTAs/SM
-  static const int variant = getenv("MDC_Q612_VARIANT") ? atoi(getenv("MDC_Q612_VARIANT")) : 0;
-  long long max_blocks = (long long)h->num_sms * (variant ? 4 : 2) * 4;   // 4 waves of resident CTAs
+  long long max_blocks = (long long)h->num_sms * 4 * 4;   // 4 waves of resident CTAs
   long long blocks = (warps_needed * 32 + threads - 1) / threads;
   if (blocks > max_blocks) blocks = max_blocks;
   const int4* d4 = reinterpret_cast<const int4*>(h->q_dense.ptr);
-  const int4* x4 = reinterpret_cast<const int4*>(x);
   prof_begin(h, stream);
-  if (h->F == 3 && h->C == 3) {
-    if (variant) q612_kernel<3, 3, false, 4><<<(unsigned)blocks, threads, 0, stream>>>(p, d4, x4, n, out, pre, cls, hist);
-    else q612_kernel<3, 3, true, 2><<<(unsigned)blocks, threads, 0, stream>>>(p, d4, x4, n, out, pre, cls, hist);
-  } else if (h->F == 10 && h->C == 3) {
-    // the 10-filter model (DenseWeights1.txt): 60 ROM rows per lane do not fit registers, they come through L1
-    q612_kernel<10, 3, false, 2><<<(unsigned)blocks, threads, 0, stream>>>(p, d4, x4, n, out, pre, cls, hist);
-  } else {
-    q612_generic_kernel<<<(unsigned)blocks, threads, 0, stream>>>(p, d4, x4, n, out, pre, cls, hist);
+  const long long piece = (1ll << 32) / kMaxClasses - 1;     // frame and output indices are 32-bit inside the kernels
+  for (long long done = 0; done < n; done += piece) {
+    const unsigned m = (unsigned)std::min(piece, n - done);
+    const int4* x4 = reinterpret_cast<const int4*>(x + done * kFrameElems);
+    int* o = out ? out + done * h->C : nullptr;
+    int* pr = pre ? pre + done * h->C : nullptr;
+    int* cl = cls ? cls + done : nullptr;
+    if (h->F == 3 && h->C == 3) {
+      q612_kernel<3, 3, 4><<<(unsigned)blocks, threads, 0, stream>>>(p, d4, x4, m, o, pr, cl, hist);
+    } else if (h->F == 10 && h->C == 3) {
+      // the 10-filter model (DenseWeights1.txt)
+      q612_kernel<10, 3, 2><<<(unsigned)blocks, threads, 0, stream>>>(p, d4, x4, m, o, pr, cl, hist);
+    } else {
+      q612_generic_kernel<<<(unsigned)blocks, threads, 0, stream>>>(p, d4, x4, (long long)m, o, pr, cl, hist);
+    }
   }
   prof_end(h, stream);
   h->launches++;

@@ -34,6 +34,11 @@ __global__ void k(unsigned long long* out, long long* cyc, float seed) {
       if (OP == 7) asm volatile("lop3.b32 %0, %0, %1, 0x20000, 0xE4;" : "+r"(u[i]) : "r"(ib));
       if (OP == 8) asm volatile("fma.rn.f32 %0, %0, 0f3F7FBE77, %0;" : "+f"(f[i]));
       if (OP == 9) asm volatile("add.s32 %0, %0, %1;" : "+r"(i32[i]) : "r"(ib));
+      if (OP == 10) asm volatile("fma.rm.f32x2 %0, %0, %1, %1;" : "+l"(a[i]) : "l"(b));
+      if (OP == 11) asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(a[i]) : "l"(b));
+      if (OP == 12) asm volatile("mul.rn.f32x2 %0, %0, %1;" : "+l"(a[i]) : "l"(b));
+      if (OP == 13) asm volatile("fma.rm.f32 %0, %0, %1, %1;" : "+f"(f[i]) : "f"(fb));
+      if (OP == 14) asm volatile("{.reg .f32 lo, hi; mov.b64 {lo, hi}, %0; max.f32 lo, lo, 0f00000000; max.f32 hi, hi, 0f00000000; mov.b64 %0, {lo, hi}; fma.rn.f32x2 %0, %0, %1, %1;}" : "+l"(a[i]) : "l"(b));
     }
   }
   const long long t1 = clock64();
@@ -71,5 +76,10 @@ int main() {
   run<6>("SHF (funnel)");
   run<7>("LOP3");
   run<9>("IADD");
+  run<10>("FFMA2.RM");
+  run<11>("FADD2");
+  run<12>("FMUL2");
+  run<13>("FFMA.RM");
+  run<14>("2 FMNMX + FFMA2 (per 3 instr)");
   return 0;
 }
