@@ -260,7 +260,9 @@ MODE_ACCURACY = {
 }
 # DRAM bytes of one conv-kernel launch at 65,536 frames from the committed ncu --set full captures
 # (dram__bytes_read.sum + dram__bytes_write.sum), not re-measured by this program
-NCU_TRAFFIC = {"bf16": (1.393e9, "profiles/r01_ncu_vt_bf16.md")}
+NCU_TRAFFIC = {"bf16": (1.393e9, "profiles/r01_ncu_vt_bf16.md"),
+               # 0.068 GB read + 2.710 GB written per 65,536 frames (1,024 B in + 2 x 21,120 B of fp16 hi/lo activations)
+               "f16x3": (2.778e9, "profiles/r02_ncu_vt_f16x3.md")}
 
 
 def run_ours(args):
@@ -495,8 +497,10 @@ def other_paths(torch, dev, peaks, _lib):
         lambda i: _lib.check(qm._h._lib.mdc_predict_q612_host(qm._h.ptr, xq_h.ctypes.data, nh, oq_h.ctypes.data, None, None, None)),
         1036, n, UNIT, peaks, torch, h2d=nh * 1024, d2h=nh * 12,
         extra={"dtype": "int18/36 in int32/int64",
-               "note": "integer-pipe-bound, not HBM-bound: ~150 half-rate IMAD per lane and frame on the small-signal "
-                       "path (300 SMSP-cycles -> ~3.8e9 frames/s ceiling at 1.9 GHz); the 36-bit exact path runs at 1.36e9"},
+               "issue_ceiling_frames_per_s": 148 * 4 * 1.965e9 / 317,
+               "note": "instruction-issue-bound, not HBM-bound: 317 warp instructions per frame on the small-signal path "
+                       "(204 of them the MACs, shifts and max of the arithmetic itself; ncu: issue slots 83 % busy, L1 90 %, "
+                       "DRAM 37 % - profiles/r02_q612.md); the 36-bit exact path runs at about half that rate"},
         host_units=nh))
     del xq, oq
 
@@ -506,6 +510,11 @@ def other_paths(torch, dev, peaks, _lib):
     pf = torch.empty((n, 3), dtype=torch.float32, device=dev)
     xf_h = torch.from_numpy(synth.iq_frames(nh)).pin_memory().numpy()
     pf_h = np.empty((nh, 3), dtype=np.float32)
+    # issue slots of the arithmetic alone, per frame and warp: an FFMA2 holds the issue port for two cycles
+    # (tools/pipe_rate), so F FFMA2-pairs cost 2 x (2F conv + 3F dense) x 4 slots plus 8F FMNMX for the ReLU
+    tiny_note = ("fp32 FMA and issue slots bind before HBM: an FFMA2 occupies its scheduler's issue port for two cycles "
+                 "(tools/pipe_rate), so the arithmetic alone needs 48 F slots per frame and warp (40 F of FFMA2, 8 F of "
+                 "FMNMX for the ReLU)")
     for tag, label, flop in (("A_3conv", "tiny_f32 F=3 (C3, 3conv checkpoint)", 7740), ("E_f10", "tiny_f32 F=10 (C2a, convmodrecnets_CNN2_0.5)", 25800)):
         w = [hw[f"{tag}_{k}"] for k in ("conv_k", "conv_b", "dense_k", "dense_b")]
         tm = tiny_cnn2(w[0].shape[-1], 3, dev.index)
@@ -516,7 +525,9 @@ def other_paths(torch, dev, peaks, _lib):
             lambda i: _lib.check(tm._h._lib.mdc_predict_f32_host(tm._h.ptr, xf_h.ctypes.data, nh, pf_h.ctypes.data, None, None, None)),
             1036, n, UNIT, peaks, torch, h2d=nh * 1024, d2h=nh * 12,
             extra={"dtype": "f32", "flop_per_frame": flop,
-                   "fp32_fma_ceiling_frames_per_s": 148 * 128 * 2 * 1.965e9 / flop}, host_units=nh))
+                   "fp32_fma_ceiling_frames_per_s": 148 * 128 * 2 * 1.965e9 / flop,
+                   "issue_ceiling_frames_per_s": 148 * 4 * 1.965e9 / (48 * w[0].shape[-1]), "note": tiny_note},
+            host_units=nh))
     # BASELINE configs[1] names the F=10 checkpoint file at batch 65,536: the same kernel at that batch size, one launch
     # per step over 32 rotating 64 MiB slices of the 2 GiB input (slices > L2 apart)
     nb = 65536
@@ -524,7 +535,8 @@ def other_paths(torch, dev, peaks, _lib):
         "tiny_f32 F=10, batch 65,536 per launch (configs[1] checkpoint file convmodrecnets_CNN2_0.5.wts.h5)", tm,
         lambda i: _lib.check(tm._h._lib.mdc_predict_f32(tm._h.ptr, xf[(i % 32) * nb:].data_ptr(), nb, pf.data_ptr(), None, None, None, stream)),
         None, 1036, nb, UNIT, peaks, torch, steps=32, warmup=4,
-        extra={"dtype": "f32", "flop_per_frame": 25800, "fp32_fma_ceiling_frames_per_s": 148 * 128 * 2 * 1.965e9 / 25800}))
+        extra={"dtype": "f32", "flop_per_frame": 25800, "fp32_fma_ceiling_frames_per_s": 148 * 128 * 2 * 1.965e9 / 25800,
+               "issue_ceiling_frames_per_s": 148 * 4 * 1.965e9 / 480, "note": tiny_note}))
     del xf, pf
 
     # 8f-4: raw RTL-SDR ingest, 2^28 samples (512 MiB of u8 in, 2 GiB f32 + 2 GiB Q6.12 frames out)

@@ -662,6 +662,9 @@ int mdc_set_weights_q612(mdc_handle_t h, const int32_t* conv_tab, const int32_t*
     if (ylim > bmax + 1) xfast = std::min(xlim, csum ? ((ylim - bmax - 1) * 4096) / csum : top);
     h->q_xfast = (int)std::min(xfast, 1ll << 17);
   }
+  // same ordering rule as ensure_packed: predictions already enqueued (the pipeline streams are non-blocking)
+  // finish with the old ROM image before it is overwritten
+  MDC_CUDA(cudaDeviceSynchronize());
   if (int e = h->q_dense.reserve(img.size() * sizeof(int))) return e;
   MDC_CUDA(cudaMemcpy(h->q_dense.ptr, img.data(), img.size() * sizeof(int), cudaMemcpyHostToDevice));
   h->have_q = true;

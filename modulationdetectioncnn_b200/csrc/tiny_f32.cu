@@ -6,14 +6,10 @@
 //   y[r][p][f] = relu(xp[r][p]*k0[f] + xp[r][p+1]*k1[f] + b[f]),  p = 0..128, xp[0]=xp[129]=0
 //   z[c]       = relu(sum_{r,p,f} y[r][p][f] * D[(r*129 + p)*F + f][c] + d[c])
 //
-// 1,036 B per frame.  A consumer warp maps lane l to positions p = 4l..4l+3 of both rows (16-B loads); position
-// 128 (which only needs x[127]) is spread over lanes 0..2F-1, one (row,filter) pair each.  The math is packed
-// FFMA2 (two positions per instruction), the Dense rows a lane needs live in shared memory (or, F=3 variant 0, in
-// registers), and the epilogue - cross-lane sums by recursive halving, softmax, argmax, class histogram - is
-// fused.  Two ways to feed the warps (template parameter STAGES): the default "direct" form (STAGES = 0: every
-// warp fetches its own R frames one block ahead with streaming 16-B loads) and a TMA ring (one producer warp
-// streaming blocks of 7R frames into shared memory with 1-D bulk copies, mbarrier full/empty per stage); see the
-// measurements at the launch site.
+// 1,036 B per frame.  A warp maps lane l to positions p = 4l..4l+3 of both rows; position 128 (which only needs
+// x[127]) is spread over lanes 0..2F-1, one (row,filter) pair each.  The math is packed FFMA2 (two positions per
+// instruction), the Dense rows a lane needs live in shared memory, and the epilogue - cross-lane sums by recursive
+// halving, softmax, argmax, class histogram - is fused.
 #include "mdc_internal.cuh"
 #include "sm100.cuh"
 
@@ -25,9 +21,6 @@ struct TinyParams {
   float bias[kMaxClasses];
   int F, C;
 };
-
-constexpr int kTinyConsumers = 7;                           // consumer warps per CTA (8 warps: 128 regs at 2 CTAs/SM)
-constexpr int kTinyThreads = (kTinyConsumers + 1) * 32;     // + the TMA producer warp
 
 __device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
   uint64_t d;
@@ -51,287 +44,12 @@ __device__ __forceinline__ uint64_t f2_relu(uint64_t v) {
 // dense image (packed on host):
 //   main [r][f][c][128]  entry p = D[(r*129 + p)*F + f][c]            -> float4 per lane
 //   tail [r][f][c]       = D[(r*129 + 128)*F + f][c]                  (position 128)
-// dynamic shared memory: ring [STAGES][8R frames][256 f32] | (WREG ? nothing : main image) | barriers
-template <int F, int C, int R, int STAGES, bool WREG, int MINB>
-__global__ void __launch_bounds__(kTinyThreads, MINB)
-tiny_f32_kernel(const TinyParams p, const float4* __restrict__ dmain, const float* __restrict__ dtail,
-                const float* __restrict__ x, long long n, float* __restrict__ probs,
-                float* __restrict__ dense, int* __restrict__ cls,
-                unsigned long long* __restrict__ hist) {
-  // STAGES == 0: "direct" variant - no ring and no producer: all eight warps are consumers and fetch their own
-  // frames from global memory, one block ahead (for compute-bound shapes: warps are not coupled through a ring)
-  constexpr bool kDirect = STAGES == 0;
-  constexpr int kCons = kDirect ? kTinyConsumers + 1 : kTinyConsumers;
-  constexpr int kBlockFrames = kCons * R;
-  constexpr int kStageBytes = kBlockFrames * 1024;
-  constexpr int kWBytes = WREG ? 0 : 2 * F * C * 128 * 4;
-  extern __shared__ __align__(128) uint8_t smem[];
-  uint8_t* ring = smem;
-  const float4* wsm = reinterpret_cast<const float4*>(smem + STAGES * kStageBytes);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * kStageBytes + kWBytes);
-  uint64_t* empty = full + STAGES;
-
-  const int lane = threadIdx.x & 31;
-  const int warp = uniform_warp_idx();
-  const long long nblocks = (n + kBlockFrames - 1) / kBlockFrames;
-
-  if (!WREG) {
-    float4* wdst = reinterpret_cast<float4*>(smem + STAGES * kStageBytes);
-    for (int i = threadIdx.x; i < 2 * F * C * 32; i += kTinyThreads) wdst[i] = __ldg(dmain + i);
-  }
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full[s], 1);
-      mbar_init(&empty[s], kTinyConsumers);
-    }
-    fence_barrier_init();
-  }
-  __syncthreads();
-
-  if (!kDirect && warp == kTinyConsumers) {
-    // ---- producer: one bulk copy per block of frames
-    uint32_t it = 0;
-    for (long long blk = blockIdx.x; blk < nblocks; blk += gridDim.x, ++it) {
-      const uint32_t s = it % (kDirect ? 1 : STAGES), ph = (it / (kDirect ? 1 : STAGES)) & 1;
-      const long long f0 = blk * kBlockFrames;
-      const long long left = n - f0;
-      const uint32_t bytes = (uint32_t)(left < kBlockFrames ? left : kBlockFrames) * 1024u;
-      mbar_wait(&empty[s], ph ^ 1);
-      if (elect_one()) {
-        mbar_arrive_expect_tx(&full[s], bytes);
-        bulk_g2s(ring + s * kStageBytes, x + f0 * 256, bytes, &full[s]);
-      }
-      __syncwarp();
-    }
-    return;
-  }
-
-  // ---- consumers
-  float4 w[WREG ? 2 * F * C : 1];
-  if (WREG) {
-#pragma unroll
-    for (int i = 0; i < 2 * F * C; ++i) w[i] = __ldg(dmain + i * 32 + lane);
-  }
-  // position 128: lane j < 2F handles (r = j / F, f = j % F)
-  float tw[C];
-  float tk0 = 0.f, tb = 0.f;
-  const int tr = lane / F;
-#pragma unroll
-  for (int c = 0; c < C; ++c) tw[c] = 0.f;
-  if (lane < 2 * F) {
-    const int tf = lane % F;
-    tk0 = p.conv[3 * tf];
-    tb = p.conv[3 * tf + 2];
-#pragma unroll
-    for (int c = 0; c < C; ++c) tw[c] = __ldg(dtail + (tr * F + tf) * C + c);
-  }
-  unsigned cnt = 0;
-
-  uint32_t it = 0;
-  float4 nxi[kDirect ? R : 1], nxq[kDirect ? R : 1];
-  auto fetch = [&](long long blk) {               // direct variant: this warp's R frames of block blk
-    const float4* x4 = reinterpret_cast<const float4*>(x);
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const long long f = blk * kBlockFrames + warp * R + r;
-      if (kDirect && blk < nblocks && f < n) {
-        asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
-                     : "=f"(nxi[r].x), "=f"(nxi[r].y), "=f"(nxi[r].z), "=f"(nxi[r].w) : "l"(x4 + f * 64 + lane));
-        asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
-                     : "=f"(nxq[r].x), "=f"(nxq[r].y), "=f"(nxq[r].z), "=f"(nxq[r].w) : "l"(x4 + f * 64 + 32 + lane));
-      } else if (kDirect) {
-        nxi[r] = nxq[r] = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    }
-  };
-  if (kDirect) fetch(blockIdx.x);
-  for (long long blk = blockIdx.x; blk < nblocks; blk += gridDim.x, ++it) {
-    const long long f0 = blk * kBlockFrames + warp * R;
-    float4 xi[R], xq[R];
-    if (kDirect) {
-#pragma unroll
-      for (int r = 0; r < R; ++r) { xi[r] = nxi[r]; xq[r] = nxq[r]; }
-      fetch(blk + gridDim.x);
-    } else {
-      const uint32_t s = it % (kDirect ? 1 : STAGES), ph = (it / (kDirect ? 1 : STAGES)) & 1;
-      mbar_wait(&full[s], ph);
-      const float4* src = reinterpret_cast<const float4*>(ring + s * kStageBytes) + warp * R * 64;
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        xi[r] = src[r * 64 + lane];
-        xq[r] = src[r * 64 + 32 + lane];
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[s]);       // frames are in registers: hand the stage back
-    }
-
-    uint64_t acc[R][C];       // {even positions, odd positions} partial sums
-    uint64_t PI01[R], PI23[R], XI01[R], XI23[R], PQ01[R], PQ23[R], XQ01[R], XQ23[R];
-    float tail[R][C];
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      float pi = __shfl_up_sync(0xffffffffu, xi[r].w, 1);
-      float pq = __shfl_up_sync(0xffffffffu, xq[r].w, 1);
-      if (lane == 0) { pi = 0.f; pq = 0.f; }
-      // y[i] = relu(x[i-1] k0 + x[i] k1 + b): pairs (y0,y1) and (y2,y3)
-      PI01[r] = f2_pack(pi, xi[r].x);       PI23[r] = f2_pack(xi[r].y, xi[r].z);
-      XI01[r] = f2_pack(xi[r].x, xi[r].y);  XI23[r] = f2_pack(xi[r].z, xi[r].w);
-      PQ01[r] = f2_pack(pq, xq[r].x);       PQ23[r] = f2_pack(xq[r].y, xq[r].z);
-      XQ01[r] = f2_pack(xq[r].x, xq[r].y);  XQ23[r] = f2_pack(xq[r].z, xq[r].w);
-      // position 128: xp[128] = x[127] (lane 31 .w), xp[129] = 0
-      const float li = __shfl_sync(0xffffffffu, xi[r].w, 31);
-      const float lq = __shfl_sync(0xffffffffu, xq[r].w, 31);
-      const float yt = fmaxf(fmaf(tr ? lq : li, tk0, tb), 0.f);
-#pragma unroll
-      for (int c = 0; c < C; ++c) {
-        tail[r][c] = (lane < 2 * F) ? yt * tw[c] : 0.f;
-        acc[r][c] = 0ull;
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < F; ++k) {
-      const uint64_t K0 = f2_pack(p.conv[3 * k], p.conv[3 * k]), K1 = f2_pack(p.conv[3 * k + 1], p.conv[3 * k + 1]);
-      const uint64_t B = f2_pack(p.conv[3 * k + 2], p.conv[3 * k + 2]);
-      float4 wi[C], wq[C];
-#pragma unroll
-      for (int c = 0; c < C; ++c) {
-        if (WREG) {
-          wi[c] = w[(0 * F + k) * C + c];
-          wq[c] = w[(1 * F + k) * C + c];
-        } else {
-          wi[c] = wsm[((0 * F + k) * C + c) * 32 + lane];
-          wq[c] = wsm[((1 * F + k) * C + c) * 32 + lane];
-        }
-      }
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        const uint64_t yi01 = f2_relu(f2_fma(K0, PI01[r], f2_fma(K1, XI01[r], B)));
-        const uint64_t yi23 = f2_relu(f2_fma(K0, PI23[r], f2_fma(K1, XI23[r], B)));
-        const uint64_t yq01 = f2_relu(f2_fma(K0, PQ01[r], f2_fma(K1, XQ01[r], B)));
-        const uint64_t yq23 = f2_relu(f2_fma(K0, PQ23[r], f2_fma(K1, XQ23[r], B)));
-#pragma unroll
-        for (int c = 0; c < C; ++c) {
-          uint64_t a = acc[r][c];
-          a = f2_fma(yi01, f2_pack(wi[c].x, wi[c].y), a);
-          a = f2_fma(yi23, f2_pack(wi[c].z, wi[c].w), a);
-          a = f2_fma(yq01, f2_pack(wq[c].x, wq[c].y), a);
-          a = f2_fma(yq23, f2_pack(wq[c].z, wq[c].w), a);
-          acc[r][c] = a;
-        }
-      }
-    }
-    if constexpr (R == 2 && C <= 4) {
-      // Cross-lane sums of the 2 x C partials by recursive halving: every step halves the values a lane carries
-      // instead of reducing each of them over all 32 lanes (9 shuffles instead of 10 C), and leaves the sum for
-      // (frame r, class c) in the lanes with bit 4 = r, bits 3..2 = c.  One softmax per warp serves both frames.
-      float v[8];
-#pragma unroll
-      for (int r = 0; r < 2; ++r)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          if (c < C) {
-            float lo, hi;
-            f2_unpack(acc[r][c], lo, hi);
-            v[r * 4 + c] = (lo + hi) + tail[r][c];
-          } else {
-            v[r * 4 + c] = 0.f;
-          }
-        }
-      const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
-      float w4[4], w2[2];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) w4[j] = (b4 ? v[4 + j] : v[j]) + __shfl_xor_sync(0xffffffffu, b4 ? v[j] : v[4 + j], 16);
-#pragma unroll
-      for (int j = 0; j < 2; ++j) w2[j] = (b3 ? w4[2 + j] : w4[j]) + __shfl_xor_sync(0xffffffffu, b3 ? w4[j] : w4[2 + j], 8);
-      float t = (b2 ? w2[1] : w2[0]) + __shfl_xor_sync(0xffffffffu, b2 ? w2[0] : w2[1], 4);
-      t += __shfl_xor_sync(0xffffffffu, t, 2);
-      t += __shfl_xor_sync(0xffffffffu, t, 1);
-      const int myc = (lane >> 2) & 3, half = lane & 16;
-      float bsel = p.bias[0];
-#pragma unroll
-      for (int c = 1; c < C; ++c) if (myc == c) bsel = p.bias[c];
-      t = fmaxf(t + bsel, 0.f);
-      float z[C];
-#pragma unroll
-      for (int c = 0; c < C; ++c) z[c] = __shfl_sync(0xffffffffu, t, half + 4 * c);
-      const long long f = f0 + (lane >> 4);
-      if (f < n) {
-        int best = 0;
-        float m = z[0];
-#pragma unroll
-        for (int c = 1; c < C; ++c) if (z[c] > m) { m = z[c]; best = c; }
-        float e[C], sum = 0.f;
-#pragma unroll
-        for (int c = 0; c < C; ++c) { e[c] = expf(z[c] - m); sum += e[c]; }
-        const float inv = 1.0f / sum;
-        const int l16 = lane & 15;                 // lane c of each half-warp writes class c of its frame
-        float zsel = z[0], psel = e[0] * inv;
-#pragma unroll
-        for (int c = 1; c < C; ++c) if (l16 == c) { zsel = z[c]; psel = e[c] * inv; }
-        if (l16 < C) {
-          if (dense) dense[f * C + l16] = zsel;
-          if (probs) probs[f * C + l16] = psel;
-        }
-        if (l16 == 0 && cls) cls[f] = best;
-        cnt += (l16 == best);
-      }
-    } else {
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      float z[C];
-#pragma unroll
-      for (int c = 0; c < C; ++c) {
-        float lo, hi;
-        f2_unpack(acc[r][c], lo, hi);
-        float a = (lo + hi) + tail[r][c];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-        z[c] = fmaxf(a + p.bias[c], 0.f);
-      }
-      const long long f = f0 + r;
-      if (f < n) {
-        int best = 0;
-        float m = z[0];
-#pragma unroll
-        for (int c = 1; c < C; ++c) if (z[c] > m) { m = z[c]; best = c; }
-        float e[C], sum = 0.f;
-#pragma unroll
-        for (int c = 0; c < C; ++c) { e[c] = expf(z[c] - m); sum += e[c]; }
-        const float inv = 1.0f / sum;
-        // lane c writes class c: one coalesced store per output instead of C single-lane stores
-        float zsel = z[0], psel = e[0] * inv;
-#pragma unroll
-        for (int c = 1; c < C; ++c) if (lane == c) { zsel = z[c]; psel = e[c] * inv; }
-        if (lane < C) {
-          if (dense) dense[f * C + lane] = zsel;
-          if (probs) probs[f * C + lane] = psel;
-        }
-        if (lane == 0 && cls) cls[f] = best;
-        cnt += (lane == best);
-      }
-    }
-    }
-  }
-  if (hist) {
-    if constexpr (R == 2 && C <= 4) {
-      // lanes c and 16 + c counted class c for the even and the odd frames of this warp
-      cnt += __shfl_xor_sync(0xffffffffu, cnt, 16);
-      if (lane < C && cnt) atomicAdd(hist + lane, (unsigned long long)cnt);
-    } else {
-      if (lane < C && cnt) atomicAdd(hist + lane, (unsigned long long)cnt);
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// Second formulation (default for the shipped shapes, F in {3, 10}, C <= 4): FOUR frames per warp pass.
 //
-// What the counters of the kernel above say (ncu, F = 10: 483 warp-instructions per frame against ~283 of useful
-// math, issue slots 64 % busy, 131 shared-memory wavefronts per frame): every lane needs its own 2 F C float4 of Dense
-// weights, so a warp pass streams the WHOLE 30 KB weight image through the LSU - 240 cycles per pass, 120 per frame at
-// two frames per pass, more than the 100 cycles per frame the FMA pipe needs; and the conv constants are packed into
-// register pairs with MOVs on every pass.  Here a pass covers four frames (60 wavefronts per frame), the conv
-// constants arrive pre-duplicated as 64-bit kernel parameters (FFMA2 reads them straight from the constant bank),
+// FOUR frames per warp pass.  (The first formulation - two frames per pass, frames through a CTA-wide TMA ring or
+// register prefetch, conv constants packed with MOVs - measured 483 warp-instructions and 131 shared-memory wavefronts
+// per frame for F = 10, profiles/r01_ncu_small.md; it was removed when this one replaced it.)  Every lane needs its own
+// 2 F C float4 of Dense weights, so a warp pass streams the WHOLE 30 KB weight image through the LSU: with four frames
+// per pass that is 60 wavefronts per frame.  The conv constants arrive pre-duplicated as 64-bit kernel parameters (FFMA2 reads them straight from the constant bank),
 // and the frames come through a per-warp ring of three 4 KB buffers filled by 1-D bulk copies (one elected lane, one
 // mbarrier per buffer, no register prefetch, no coupling between warps: a warp refills the buffer it has just read).
 struct TinyParams4 {
@@ -654,34 +372,6 @@ int launch_tiny_f32(mdc_handle_s* h, const float* x, int64_t n, float* probs, fl
     long long max_blocks = (long long)h->num_sms * 2 * 4;
     return (unsigned)(blocks > max_blocks ? max_blocks : blocks);
   };
-  // variant selection (MDC_TINY_VARIANT, tuning aid).  Measured on B200, 2^21 frames, frames/s:
-  //   3           direct loads, no ring, 8 consumer warps, 2 CTAs/SM     F=3: 3.42e9   F=10: 1.51e9
-  //   2           direct loads, 3 CTAs/SM (80 registers, small spills)   F=3: 3.39e9   F=10: 1.45e9
-  //   1           TMA ring, Dense rows in shared memory, 3 CTAs/SM       F=3: 3.14e9   F=10: 1.32e9
-  //   0           TMA ring, Dense rows in registers (F=3) / 2 CTAs/SM    F=3: 2.55e9   F=10: 1.21e9
-  // The ring keeps more bytes in flight, but these kernels are issue-bound, not latency-bound, and the ring couples
-  // the consumer warps of a CTA (a stage is refilled only when the slowest of seven warps has taken its frames:
-  // 15 % of the consumers' samples sat in the full-barrier wait) and spends a warp on the producer.
-  //   4 (default) tiny_f32_kernel4: four frames per warp pass, per-warp bulk-copy ring, 14 warps, 1 CTA/SM
-  static const int variant = getenv("MDC_TINY_VARIANT") ? atoi(getenv("MDC_TINY_VARIANT")) : 4;
-  auto ring_grid = [&](int R, int ctas_per_sm, int cons = kTinyConsumers) {
-    const long long nblocks = (n + cons * R - 1) / (cons * R);
-    const long long max_blocks = (long long)h->num_sms * ctas_per_sm;
-    return (unsigned)(nblocks > max_blocks ? max_blocks : nblocks);
-  };
-#define MDC_TINY_LAUNCH(F_, C_, R_, S_, WREG_, MINB_)                                                        \
-  do {                                                                                                      \
-    constexpr int smem_ = S_ * kTinyConsumers * R_ * 1024 + (WREG_ ? 0 : 2 * F_ * C_ * 128 * 4) + 2 * S_ * 8; \
-    static bool attr_ = false;                                                                              \
-    if (!attr_) {                                                                                           \
-      MDC_CUDA(cudaFuncSetAttribute(tiny_f32_kernel<F_, C_, R_, S_, WREG_, MINB_>,                          \
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, smem_));                   \
-      attr_ = true;                                                                                         \
-    }                                                                                                       \
-    tiny_f32_kernel<F_, C_, R_, S_, WREG_, MINB_><<<ring_grid(R_, MINB_, S_ == 0 ? kTinyConsumers + 1 : kTinyConsumers),     \
-                                                    kTinyThreads, smem_, stream>>>(                         \
-        p, dm, dt, x, n, probs, dense, cls, hist);                                                          \
-  } while (0)
 #define MDC_TINY4_LAUNCH(F_, C_, W_, B_)                                                                      \
   do {                                                                                                        \
     using Cfg_ = Tiny4<F_, C_, W_, B_>;                                                                       \
@@ -711,20 +401,10 @@ int launch_tiny_f32(mdc_handle_s* h, const float* x, int64_t n, float* probs, fl
   prof_begin(h, stream);
   // 16 warps x 3 buffers: measured against 14 warps (F = 10: 1.60e9 -> 1.84e9 frames/s - the kernel wants warps to
   // fill the FMA pipe's off-cycles); 18+ warps would leave < 128 registers per thread and spill
-  if (F == 3 && C == 3 && variant >= 4) {
+  if (F == 3 && C == 3) {
     MDC_TINY4_LAUNCH(3, 3, 16, 3);
-  } else if (F == 10 && C == 3 && variant >= 4) {
-    MDC_TINY4_LAUNCH(10, 3, 16, 3);
-  } else if (F == 3 && C == 3) {
-    if (variant == 3) MDC_TINY_LAUNCH(3, 3, 2, 0, false, 2);
-    else if (variant == 2) MDC_TINY_LAUNCH(3, 3, 2, 0, false, 3);
-    else if (variant == 1) MDC_TINY_LAUNCH(3, 3, 2, 4, false, 3);
-    else MDC_TINY_LAUNCH(3, 3, 1, 12, true, 2);
   } else if (F == 10 && C == 3) {
-    if (variant == 3) MDC_TINY_LAUNCH(10, 3, 2, 0, false, 2);
-    else if (variant == 2) MDC_TINY_LAUNCH(10, 3, 2, 0, false, 3);
-    else if (variant == 1) MDC_TINY_LAUNCH(10, 3, 2, 3, false, 3);
-    else MDC_TINY_LAUNCH(10, 3, 2, 4, false, 2);
+    MDC_TINY4_LAUNCH(10, 3, 16, 3);
   } else {
     tiny_f32_generic_kernel<<<grid(1), threads, 0, stream>>>(
         p, reinterpret_cast<const float*>(h->tiny_dense.ptr), dt, x4, n, probs, dense, cls, hist);

@@ -34,6 +34,6 @@ for tag in ("A_3conv", "E_f10"):
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / reps
-        print(f"variant {os.environ.get('MDC_TINY_VARIANT', 'default')} F={w[0].shape[-1]} n={nn}: {ms * 1e3:.1f} us  "
+        print(f"F={w[0].shape[-1]} n={nn}: {ms * 1e3:.1f} us  "
               f"{nn / ms * 1e3:.3e} frames/s  {nn * 1036 / ms / 1e6:.0f} GB/s", flush=True)
     m.close()
