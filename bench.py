@@ -145,6 +145,13 @@ def _reference_frames_per_step(rate: float, total_steps: int) -> int:
     return int(min(BATCH, max(256, rate * budget / total_steps))) // 256 * 256
 
 
+def workload_config(frames_per_step):
+    """The part of `config` both arms share (BASELINE.json configs[1])."""
+    return {"workload": "VT-CNN2 11-class (BASELINE configs[1] / SURVEY C2b), 2x128 I/Q frames",
+            "frames_per_gpu_per_step": frames_per_step, "weights": "synthetic Glorot/He, Philox(1602)",
+            "input": "N(0, 2^-7) float32, seeded"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
@@ -175,9 +182,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "VT-CNN2 11-class (C2b), synthetic 2x128 I/Q", "frames_per_step": n,
-                   "weights": "synthetic Philox(1602)", "note": "Keras/TensorFlow are not installable here; "
-                   "torch-CPU runs the same layer stack on all host cores"},
+        "config": {**workload_config(n), "mode": "fp32", "precision": "fp32 (oneDNN/MKL)",
+                   "note": "Keras/TensorFlow are not installable here; torch-CPU runs the same layer stack on all host "
+                           "cores; inputs from the same Philox stream as the parity tests"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -422,9 +429,7 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": {"bf16": "bf16", "tf32x3": "tf32x3", "f16x3": "f16x3", "fp32": "f32"}[mode], "data": "synthetic",
-        "config": {"workload": "VT-CNN2 11-class (BASELINE configs[1] / SURVEY C2b), 2x128 I/Q frames",
-                   "frames_per_gpu_per_step": batch, "weights": "synthetic Glorot/He, Philox(1602)",
-                   "input": "N(0, 2^-7) float32, torch.Generator(seed 2016+rank)", "mode": mode,
+        "config": {**workload_config(batch), "mode": mode,
                    "precision": MODE_ACCURACY[mode],
                    "l2": f"{N_INPUT_BUFFERS} distinct input buffers rotated ({N_INPUT_BUFFERS * batch * 1024 >> 20} MiB > 126 MB L2)",
                    "parallelism": f"frame-sharded dp{world}, one NCCL all-reduce of int64[11] histogram",

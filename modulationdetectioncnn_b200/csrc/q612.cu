@@ -277,7 +277,7 @@ int launch_q612(mdc_handle_s* h, const int32_t* x, int64_t n, int32_t* out, int3
       q612_kernel<3, 3, 4><<<(unsigned)blocks, threads, 0, stream>>>(p, d4, x4, m, o, pr, cl, hist);
     } else if (h->F == 10 && h->C == 3) {
       // the 10-filter model (DenseWeights1.txt)
-      q612_kernel<10, 3, 2><<<(unsigned)blocks, threads, 0, stream>>>(p, d4, x4, m, o, pr, cl, hist);
+      q612_kernel<10, 3, 4><<<(unsigned)blocks, threads, 0, stream>>>(p, d4, x4, m, o, pr, cl, hist);
     } else {
       q612_generic_kernel<<<(unsigned)blocks, threads, 0, stream>>>(p, d4, x4, (long long)m, o, pr, cl, hist);
     }

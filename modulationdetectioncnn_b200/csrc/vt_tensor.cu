@@ -1045,7 +1045,8 @@ static_assert(kVtFlat % kHK == 0 && kHKBlocks % kHRunBlocks == 0, "K blocks / ru
 struct DenseF16Smem {
   static constexpr int stages = 0;
   static constexpr int b3 = kHStages * kHStageBytes;
-  static constexpr int bars = b3 + 1024;
+  static constexpr int zx = b3 + 1024;                 // fused head: partial logits of the upper column half, 2 tiles
+  static constexpr int bars = zx + 2 * kTM * kMaxClasses * 4;
   // full[S], empty[S], hh_full, hh_empty, cross_empty
   static constexpr int nbars = 2 * kHStages + 3;
   static constexpr int tmem_slot = bars + nbars * 8;
@@ -1053,10 +1054,27 @@ struct DenseF16Smem {
 };
 static_assert(DenseF16Smem::total <= 232448, "f16x3 dense kernel shared memory exceeds 227 KB");
 
+// Partial logits of one frame over this thread's 128 dense1 outputs (column half H): +b3, ReLU, Dense(C) with every
+// W4 element an immediate-offset constant-bank operand (H is a template parameter for exactly that reason).
+template <int C, int H>
+__device__ __forceinline__ void head_partial(const float (&acc)[128], const float* b3s, const HeadW<C>& hw, float (&z)[C]) {
+#pragma unroll
+  for (int e = 0; e < 128; ++e) {
+    const float hv = fmaxf(acc[e] + b3s[e], 0.f);
+#pragma unroll
+    for (int c = 0; c < C; ++c) z[c] = fmaf(hv, hw.w[(H * 128 + e) * C + c], z[c]);
+  }
+}
+
+// C > 0: the rest of the network is fused into the epilogue (Dense(C), softmax, argmax, histogram; h never goes to HBM
+// and the separate head launch is gone).  C == 0: h is stored to hbuf and vt_head_kernel follows (any class count).
+template <int C>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDenseT32Threads, 1)
 vt_dense_f16x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
                       const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUtensorMap map_bl,
-                      const float* __restrict__ b3g, float* __restrict__ hbuf, long long n, int num_tiles) {
+                      const __grid_constant__ HeadW<(C > 0 ? C : 1)> hw, const float* __restrict__ b3g,
+                      float* __restrict__ hbuf, long long n, int num_tiles, float* __restrict__ probs,
+                      float* __restrict__ logits_out, int* __restrict__ cls, unsigned long long* __restrict__ hist) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DenseF16Smem::bars);
@@ -1172,7 +1190,8 @@ vt_dense_f16x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_c
     // ================= epilogue: fold the hi*hi runs into fp32 master sums, add the cross sums, +b3, ReLU -> h
     const int q = warp & 3, half = (warp - 2) >> 2;          // TMEM lane quarter, column half
     const float* b3s = reinterpret_cast<const float*>(smem + DenseF16Smem::b3) + half * 128;
-    uint32_t run = 0;
+    uint32_t run = 0, titer = 0;
+    unsigned cnt = 0;
     auto release = [&](uint64_t* bar) {           // one arrival per epilogue warp on the LEADER's barrier
       tc_fence_before_sync();
       __syncwarp();
@@ -1219,19 +1238,69 @@ vt_dense_f16x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_c
       }
       release(cross_empty);
       const long long row = (long long)tile * kTM + q * 32 + lane;
-      if (row < n) {
-        float* dst = hbuf + row * 256 + half * 128;
+      if constexpr (C == 0) {
+        if (row < n) {
+          float* dst = hbuf + row * 256 + half * 128;
 #pragma unroll
-        for (int e = 0; e < 128; e += 4) {
-          float4 o;
-          o.x = fmaxf(acc[e] + b3s[e], 0.f);
-          o.y = fmaxf(acc[e + 1] + b3s[e + 1], 0.f);
-          o.z = fmaxf(acc[e + 2] + b3s[e + 2], 0.f);
-          o.w = fmaxf(acc[e + 3] + b3s[e + 3], 0.f);
-          *reinterpret_cast<float4*>(dst + e) = o;
+          for (int e = 0; e < 128; e += 4) {
+            float4 o;
+            o.x = fmaxf(acc[e] + b3s[e], 0.f);
+            o.y = fmaxf(acc[e + 1] + b3s[e + 1], 0.f);
+            o.z = fmaxf(acc[e + 2] + b3s[e + 2], 0.f);
+            o.w = fmaxf(acc[e + 3] + b3s[e + 3], 0.f);
+            *reinterpret_cast<float4*>(dst + e) = o;
+          }
+        }
+      } else {
+        // the rest of the network, under the next tile's MMAs (the accumulators were released above): each thread has
+        // 128 of its frame's 256 dense1 outputs; the upper half hands its partial logits over through shared memory
+        float z[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) z[c] = half == 0 ? hw.b[c] : 0.f;
+        if (half == 0) head_partial<C, 0>(acc, b3s, hw, z);
+        else head_partial<C, 1>(acc, b3s, hw, z);
+        float* zx = reinterpret_cast<float*>(smem + DenseF16Smem::zx) + (titer & 1) * (kTM * C) + (q * 32 + lane) * C;
+        if (half == 1) {
+#pragma unroll
+          for (int c = 0; c < C; ++c) zx[c] = z[c];
+        }
+        // the eight epilogue warps; the buffer alternates per tile, so one barrier per tile orders its reuse as well
+        asm volatile("bar.sync 1, %0;" ::"n"(kTEpiWarps * 32) : "memory");
+        if (half == 0) {
+#pragma unroll
+          for (int c = 0; c < C; ++c) z[c] += zx[c];
+          float mx = z[0];
+          int best = 0;
+#pragma unroll
+          for (int c = 1; c < C; ++c) if (z[c] > mx) { mx = z[c]; best = c; }
+          if (row >= n) best = -1;
+          if (row < n) {
+            if (logits_out) {
+#pragma unroll
+              for (int c = 0; c < C; ++c) logits_out[row * C + c] = z[c];
+            }
+            if (probs) {
+              float e[C], sum = 0.f;
+#pragma unroll
+              for (int c = 0; c < C; ++c) { e[c] = expf(z[c] - mx); sum += e[c]; }
+              const float inv = 1.0f / sum;
+#pragma unroll
+              for (int c = 0; c < C; ++c) probs[row * C + c] = e[c] * inv;
+            }
+            if (cls) cls[row] = best;
+          }
+          if (hist) {
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+              const unsigned votes = __popc(__ballot_sync(0xffffffffu, best == c));
+              if (lane == c) cnt += votes;
+            }
+          }
         }
       }
+      ++titer;
     }
+    if (C > 0 && hist && half == 0 && lane < C && cnt) atomicAdd(hist + lane, (unsigned long long)cnt);
   }
 
   // ---- teardown (the pair leaves together: the leader's MMAs read the peer's shared memory)
@@ -1422,7 +1491,8 @@ int pack_vt_bf16(mdc_handle_s* h) {      // the tensor-core modes (MDC_MODE_BF16
   MDC_CUDA(cudaFuncSetAttribute(vt_conv_kernel<kConvTF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<kConvTF32>::total));
   MDC_CUDA(cudaFuncSetAttribute(vt_conv_kernel<kConvF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<kConvF16>::total));
   MDC_CUDA(cudaFuncSetAttribute(vt_dense_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DenseT32Smem::total));
-  MDC_CUDA(cudaFuncSetAttribute(vt_dense_f16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DenseF16Smem::total));
+  MDC_CUDA(cudaFuncSetAttribute(vt_dense_f16x3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, DenseF16Smem::total));
+  MDC_CUDA(cudaFuncSetAttribute(vt_dense_f16x3_kernel<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, DenseF16Smem::total));
   if (cm == kConvBF16) {
     switch (h->C) {
 #define MDC_DENSE_ATTR(CC) \
@@ -1550,8 +1620,18 @@ int launch_vt_dense_head(mdc_handle_s* h, int64_t m, float* probs, float* dense,
     const uint16_t* act = reinterpret_cast<const uint16_t*>(h->ws_act.ptr);
     if (int e = make_kmajor_map(&map_ah, act, (uint64_t)m, kElemF16, kTM)) return e;
     if (int e = make_kmajor_map(&map_al, act + h->vt_act_elems, (uint64_t)m, kElemF16, kTM)) return e;
-    vt_dense_f16x3_kernel<<<grid_d, kDenseT32Threads, DenseF16Smem::total, stream>>>(map_ah, map_al, wmaps[0], wmaps[1],
-                                                                                      b3, hb, m, tiles);
+    if (h->C == 11) {     // the VT-CNN2 class count: Dense(11) + softmax fused into the epilogue, no head launch
+      HeadW<11> hw;
+      memcpy(hw.w, h->w[MDC_T_DENSE2_K].data(), sizeof(hw.w));     // Keras (256, C) row-major
+      memcpy(hw.b, h->w[MDC_T_DENSE2_B].data(), sizeof(hw.b));
+      vt_dense_f16x3_kernel<11><<<grid_d, kDenseT32Threads, DenseF16Smem::total, stream>>>(
+          map_ah, map_al, wmaps[0], wmaps[1], hw, b3, nullptr, m, tiles, probs, dense, cls, hist);
+      h->launches += 1;
+      MDC_CUDA(cudaGetLastError());
+      return MDC_OK;
+    }
+    vt_dense_f16x3_kernel<0><<<grid_d, kDenseT32Threads, DenseF16Smem::total, stream>>>(
+        map_ah, map_al, wmaps[0], wmaps[1], HeadW<1>{}, b3, hb, m, tiles, nullptr, nullptr, nullptr, nullptr);
   } else {
     const float* act = reinterpret_cast<const float*>(h->ws_act.ptr);
     if (int e = make_kmajor_map(&map_ah, act, (uint64_t)m, kElemF32, kTM)) return e;
