@@ -76,6 +76,9 @@ tiny_f32_kernel4(const __grid_constant__ TinyParams4 p, const float4* __restrict
   using Cfg = Tiny4<F, C, W, B>;
   constexpr int R = Cfg::R, kBufs = Cfg::kBufs;
   extern __shared__ __align__(128) uint8_t smem[];
+  // let the next launch on the stream start its own prologue (weight image to shared memory, barriers) on SMs as this
+  // grid's CTAs retire: back-to-back launches of 65,536 frames last 20-40 us, a 5 us gap + prologue is 15-25 % of that
+  asm volatile("griddepcontrol.launch_dependents;");
   const float4* wsm = reinterpret_cast<const float4*>(smem);
   const int lane = threadIdx.x & 31, warp = uniform_warp_idx();
   uint8_t* myring = smem + Cfg::ring + warp * (kBufs * R * 1024);
@@ -118,6 +121,9 @@ tiny_f32_kernel4(const __grid_constant__ TinyParams4 p, const float4* __restrict
     }
     __syncwarp();
   };
+  // Programmatic dependent launch: everything above touched only the handle's weight images, which no kernel on the
+  // stream writes; from here on the kernel reads frames and writes outputs that the preceding kernel may own.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   // kBufs - 1 passes in flight
   issue(g, 0);
   if (kBufs > 2) issue(g + stride, 1);
@@ -383,7 +389,17 @@ int launch_tiny_f32(mdc_handle_s* h, const float* x, int64_t n, float* probs, fl
     const long long ngroups_ = (n + Cfg_::R - 1) / Cfg_::R;                                                   \
     const long long blocks_ = (ngroups_ + Cfg_::kWarps - 1) / Cfg_::kWarps;                                   \
     const unsigned grid_ = (unsigned)(blocks_ < h->num_sms ? blocks_ : h->num_sms);                           \
-    tiny_f32_kernel4<F_, C_, W_, B_><<<grid_, Cfg_::kThreads, Cfg_::total, stream>>>(p4, dm, dt, x, n, probs, dense, cls, hist); \
+    cudaLaunchConfig_t cfg_ = {};                                                                             \
+    cfg_.gridDim = dim3(grid_);                                                                               \
+    cfg_.blockDim = dim3(Cfg_::kThreads);                                                                     \
+    cfg_.dynamicSmemBytes = Cfg_::total;                                                                      \
+    cfg_.stream = stream;                                                                                     \
+    cudaLaunchAttribute pdl_[1];                                                                              \
+    pdl_[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                          \
+    pdl_[0].val.programmaticStreamSerializationAllowed = 1;                                                   \
+    cfg_.attrs = pdl_;                                                                                        \
+    cfg_.numAttrs = 1;                                                                                        \
+    MDC_CUDA(cudaLaunchKernelEx(&cfg_, tiny_f32_kernel4<F_, C_, W_, B_>, p4, dm, dt, x, (long long)n, probs, dense, cls, hist)); \
   } while (0)
   TinyParams4 p4;
   for (int f = 0; f < kMaxFilters; ++f) {
