@@ -237,7 +237,7 @@ def time_host(fn, steps, warmup, torch, dist_on):
 
 
 def hbm_path(name, handle_like, call_dev, call_host, bytes_per_unit, units, unit_name, peaks, torch, steps=5, warmup=3,
-             h2d=0, d2h=0, extra=None, host_units=None):
+             h2d=0, d2h=0, extra=None, host_units=None, host_formats=None):
     """One HBM-bound path: device-resident throughput + roofline + e2e."""
     ms = time_device(lambda i: call_dev(i), steps, warmup, torch, False)
     per = ms / steps
@@ -251,6 +251,11 @@ def hbm_path(name, handle_like, call_dev, call_host, bytes_per_unit, units, unit
         hms = time_host(lambda i: call_host(i), 3, 1, torch, False) / 3
         out["e2e"] = {"value": host_units / (hms * 1e-3), "unit": unit_name, "h2d_bytes_per_step": h2d,
                       "d2h_bytes_per_step": d2h, "units_per_step": host_units}
+        # the same blocking host call fed with the narrow frame formats (converted in the kernel's frame load)
+        for key, (fn, fmt_h2d, api) in (host_formats or {}).items():
+            fms = time_host(lambda i: fn(i), 3, 1, torch, False) / 3
+            out["e2e"][key] = {"value": host_units / (fms * 1e-3), "unit": unit_name, "h2d_bytes_per_step": fmt_h2d,
+                               "d2h_bytes_per_step": d2h, "api": api}
     if extra:
         out.update(extra)
     return out
@@ -497,6 +502,15 @@ def other_paths(torch, dev, peaks, _lib):
     nh = 1 << 18
     xq_h = torch.from_numpy(synth.q612_frames(nh)).pin_memory().numpy()
     oq_h = np.empty((nh, 3), dtype=np.int32)
+    xq16_h = torch.from_numpy(synth.q612_frames(nh).astype(np.int16)).pin_memory().numpy()
+    xu8_h = torch.randint(0, 256, (nh, 128, 2), dtype=torch.uint8).pin_memory().numpy()
+    qlib = qm._h._lib
+    q_formats = {
+        "i16": (lambda i: _lib.check(qlib.mdc_predict_q612_raw_host(qm._h.ptr, xq16_h.ctypes.data, _lib.IN_I16, nh, oq_h.ctypes.data, None, None, None)),
+                nh * 512, "mdc_predict_q612_raw_host(MDC_IN_I16): int16 Q6.12 frames in the test_table address map"),
+        "u8": (lambda i: _lib.check(qlib.mdc_predict_q612_raw_host(qm._h.ptr, xu8_h.ctypes.data, _lib.IN_U8IQ, nh, oq_h.ctypes.data, None, None, None)),
+               nh * 256, "mdc_predict_q612_raw_host(MDC_IN_U8IQ): raw RTL-SDR bytes, sample = (2u - 255) * 16"),
+    }
     out.append(hbm_path(
         "q612_sv_exact (C1, weight set A)", qm,
         lambda i: _lib.check(qm._h._lib.mdc_predict_q612(qm._h.ptr, xq.data_ptr(), n, oq.data_ptr(), None, None, hq.data_ptr(), stream)),
@@ -507,7 +521,7 @@ def other_paths(torch, dev, peaks, _lib):
                "note": "instruction-issue-bound, not HBM-bound: 317 warp instructions per frame on the small-signal path "
                        "(204 of them the MACs, shifts and max of the arithmetic itself; ncu: issue slots 83 % busy, L1 90 %, "
                        "DRAM 37 % - profiles/r02_q612.md); the 36-bit exact path runs at about half that rate"},
-        host_units=nh))
+        host_units=nh, host_formats=q_formats))
     del xq, oq
 
     # C2a / C3: TinyCNN2 fp32 from the real checkpoints
@@ -533,7 +547,9 @@ def other_paths(torch, dev, peaks, _lib):
             extra={"dtype": "f32", "flop_per_frame": flop,
                    "fp32_fma_ceiling_frames_per_s": 148 * 128 * 2 * 1.965e9 / flop,
                    "issue_ceiling_frames_per_s": 148 * 4 * 1.965e9 / (48 * w[0].shape[-1]), "note": tiny_note},
-            host_units=nh))
+            host_units=nh,
+            host_formats={"u8": (lambda i: _lib.check(tm._h._lib.mdc_predict_raw_host(tm._h.ptr, xu8_h.ctypes.data, _lib.IN_U8IQ, nh, pf_h.ctypes.data, None, None, None)),
+                                 nh * 256, "mdc_predict_raw_host(MDC_IN_U8IQ): raw RTL-SDR bytes, (u - 127.5) / 128")}))
     # BASELINE configs[1] names the F=10 checkpoint file at batch 65,536: the same kernel at that batch size, one launch
     # per step over 32 rotating 64 MiB slices of the 2 GiB input (slices > L2 apart)
     nb = 65536

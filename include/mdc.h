@@ -65,13 +65,16 @@ enum {
                           at ~2x the TF32X3 rate.  Values must stay inside the fp16 range (MDC_ERR_RANGE otherwise) */
 };
 
-/* frame formats of the mdc_predict_raw* calls (VT-CNN2 tensor-core modes convert them inside the frame load) */
+/* frame formats of the mdc_predict_raw* / mdc_predict_q612_raw* calls (converted inside the kernels' frame load:
+ * VT-CNN2 tensor-core modes, the specialised TinyCNN2 fp32 kernels F in {3,10}, C = 3, and the integer kernel) */
 enum {
   MDC_IN_F32 = 0,  /* f32 [n,2,128], row 0 = I, row 1 = Q: what model.predict receives (cnn.py:198)            */
   MDC_IN_U8IQ = 1, /* u8 [n,128,2]: raw RTL-SDR bytes I0 Q0 I1 Q1 ... (README.md:5); value = (u - 127.5)/128,
                       identical to mdc_sdr_ingest_u8 followed by mdc_predict_f32.  256 B per frame               */
-  MDC_IN_I16 = 2   /* i16 [n,256]: Q6.12 samples in the test_table address map (0-127 I, 128-255 Q,
+  MDC_IN_I16 = 2,  /* i16 [n,256]: Q6.12 samples in the test_table address map (0-127 I, 128-255 Q,
                       cnn_test_latest1.sv:88-102), value = s / 4096.  512 B per frame                             */
+  MDC_IN_I32 = 3   /* i32 [n,256]: the 18-bit words of test_table as mdc_predict_q612 takes them (integer model
+                      only).  1,024 B per frame                                                                   */
 };
 
 /* tensor ids for mdc_set_weights_f32 (Keras layouts: conv (kh,kw,cin,cout), dense (in,out)) */
@@ -185,6 +188,18 @@ MDC_API int mdc_predict_q612_host(mdc_handle_t h, const int32_t* x_host, int64_t
 MDC_API int mdc_predict_q612_host_async(mdc_handle_t h, const int32_t* x_host, int64_t n,
                                         int32_t* out_host, int32_t* pre_host, int32_t* cls_host,
                                         unsigned long long* hist_host, int64_t* ticket);
+/* The same three calls with the frame format as an argument (what feeds test_table in a deployment is an ADC, not
+ * 32-bit words): MDC_IN_I32 (as above), MDC_IN_I16 (int16 [n,256], same address map, sv:88-102: half the bytes) or
+ * MDC_IN_U8IQ (raw RTL-SDR bytes, README.md:5; sample = (2u - 255) * 16, the Q6.12 value of (u - 127.5) / 128 -
+ * identical to mdc_sdr_ingest_u8 followed by mdc_predict_q612: a quarter of the bytes).  Converted in the frame load. */
+MDC_API int mdc_predict_q612_raw(mdc_handle_t h, const void* x_dev, int in_format, int64_t n, int32_t* out_dev,
+                                 int32_t* pre_dev, int32_t* cls_dev, unsigned long long* hist_dev, void* stream);
+MDC_API int mdc_predict_q612_raw_host(mdc_handle_t h, const void* x_host, int in_format, int64_t n,
+                                      int32_t* out_host, int32_t* pre_host, int32_t* cls_host,
+                                      unsigned long long* hist_host);
+MDC_API int mdc_predict_q612_raw_host_async(mdc_handle_t h, const void* x_host, int in_format, int64_t n,
+                                            int32_t* out_host, int32_t* pre_host, int32_t* cls_host,
+                                            unsigned long long* hist_host, int64_t* ticket);
 
 /* ---- Walsh-Hadamard transform ----------------------------------------------------------
  * Replaces: the FWHT spectrogram stage named in README.md:5 (no code in the reference).

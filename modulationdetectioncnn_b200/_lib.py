@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(HERE, "libmdc.so")
 MDC_OK = 0
 MODEL_TINY, MODEL_VT = 0, 1
 MODE_FP32, MODE_BF16, MODE_TF32X3, MODE_Q612, MODE_F16X3 = 0, 1, 2, 3, 4
-IN_F32, IN_U8IQ, IN_I16 = 0, 1, 2
+IN_F32, IN_U8IQ, IN_I16, IN_I32 = 0, 1, 2, 3
 ERR_RANGE = -5
 T_CONV1_K, T_CONV1_B, T_CONV2_K, T_CONV2_B, T_DENSE1_K, T_DENSE1_B, T_DENSE2_K, T_DENSE2_B = range(8)
 OPT_FLATTEN_ORDER = 0
@@ -25,6 +25,7 @@ FWHT_NATURAL, FWHT_SEQUENCY = 0, 1
 EXPORTS = [
     "mdc_create", "mdc_destroy", "mdc_set_option", "mdc_set_weights_f32", "mdc_set_weights_q612",
     "mdc_predict_f32", "mdc_predict_f32_host", "mdc_predict_f32_host_async", "mdc_host_wait", "mdc_predict_q612", "mdc_predict_q612_host_async", "mdc_predict_q612_host",
+    "mdc_predict_q612_raw", "mdc_predict_q612_raw_host", "mdc_predict_q612_raw_host_async",
     "mdc_fwht_i32", "mdc_fwht_i32_host", "mdc_sdr_ingest_u8", "mdc_confusion_i32", "mdc_confusion_grouped_i32", "mdc_last_error", "mdc_version",
     "mdc_launch_count", "mdc_profile_enable", "mdc_profile_read", "mdc_debug_read",
     "mdc_reserve", "mdc_predict_raw", "mdc_predict_raw_host", "mdc_predict_raw_host_async", "mdc_range_flags",
@@ -63,6 +64,9 @@ def load() -> C.CDLL:
         "mdc_predict_q612": (i32, [vp, vp, i64, vp, vp, vp, vp, vp]),
         "mdc_predict_q612_host": (i32, [vp, vp, i64, vp, vp, vp, vp]),
         "mdc_predict_q612_host_async": (i32, [vp, vp, i64, vp, vp, vp, vp, C.POINTER(i64)]),
+        "mdc_predict_q612_raw": (i32, [vp, vp, i32, i64, vp, vp, vp, vp, vp]),
+        "mdc_predict_q612_raw_host": (i32, [vp, vp, i32, i64, vp, vp, vp, vp]),
+        "mdc_predict_q612_raw_host_async": (i32, [vp, vp, i32, i64, vp, vp, vp, vp, C.POINTER(i64)]),
         "mdc_fwht_i32": (i32, [vp, vp, i64, i32, i32, vp]),
         "mdc_fwht_i32_host": (i32, [vp, vp, i64, i32, i32, i32]),
         "mdc_sdr_ingest_u8": (i32, [vp, i64, vp, vp, vp, vp]),

@@ -282,15 +282,22 @@ static size_t frame_bytes(int in_fmt) { return in_fmt == MDC_IN_U8IQ ? 256 : (in
 static int check_format(const mdc_handle_s* h, int in_fmt) {
   MDC_REQUIRE(in_fmt == MDC_IN_F32 || in_fmt == MDC_IN_U8IQ || in_fmt == MDC_IN_I16, MDC_ERR_INVALID,
               "unknown frame format %d", in_fmt);
-  MDC_REQUIRE(in_fmt == MDC_IN_F32 || vt_tensor_mode(h), MDC_ERR_UNSUPPORTED,
-              "raw u8 / int16 frames are read by the VT-CNN2 tensor-core kernels only (BF16, F16X3, TF32X3); "
-              "use mdc_sdr_ingest_u8 in front of this model");
+  const bool tiny_special = h->model == MDC_MODEL_TINY && (h->F == 3 || h->F == 10) && h->C == 3;
+  MDC_REQUIRE(in_fmt == MDC_IN_F32 || vt_tensor_mode(h) || tiny_special, MDC_ERR_UNSUPPORTED,
+              "raw u8 / int16 frames are read by the VT-CNN2 tensor-core kernels (BF16, F16X3, TF32X3) and the "
+              "specialised TinyCNN2 kernels (F in {3, 10}, C = 3) only; use mdc_sdr_ingest_u8 in front of this model");
+  return MDC_OK;
+}
+
+static int check_q612_format(int in_fmt) {
+  MDC_REQUIRE(in_fmt == MDC_IN_I32 || in_fmt == MDC_IN_I16 || in_fmt == MDC_IN_U8IQ, MDC_ERR_INVALID,
+              "frame format %d: the integer model takes MDC_IN_I32, MDC_IN_I16 or MDC_IN_U8IQ", in_fmt);
   return MDC_OK;
 }
 
 static int predict_f32_dev(mdc_handle_s* h, const void* x, int in_fmt, int64_t n, float* probs, float* dense,
                            int32_t* cls, unsigned long long* hist, cudaStream_t stream) {
-  if (h->model == MDC_MODEL_TINY) return launch_tiny_f32(h, (const float*)x, n, probs, dense, cls, hist, stream);
+  if (h->model == MDC_MODEL_TINY) return launch_tiny_f32(h, x, in_fmt, n, probs, dense, cls, hist, stream);
   if (h->mode == MDC_MODE_FP32) return launch_vt_f32(h, (const float*)x, n, probs, dense, cls, hist, stream);
   return launch_vt_bf16(h, x, in_fmt, n, probs, dense, cls, hist, stream);
 }
@@ -366,9 +373,10 @@ struct OutStage {
 
 // Slot counters run on across calls, so a later call's first chunks wait for the slots an earlier call's tail
 // still uses.
-template <class In, class O0, class O1, class Launch>
-static int run_host_pipeline(mdc_handle_s* h, const In* x, int64_t n, O0* o0, O1* o1, int32_t* cls,
+template <class O0, class O1, class Launch>
+static int run_host_pipeline(mdc_handle_s* h, const void* xv, size_t fb, int64_t n, O0* o0, O1* o1, int32_t* cls,
                              unsigned long long* hist, int64_t chunk, int64_t* ticket, Launch launch) {
+  const uint8_t* x = reinterpret_cast<const uint8_t*>(xv);     // fb bytes per frame
   if (!h->pipe) h->pipe = new HostPipe();
   HostPipe& P = *h->pipe;
   if (int e = P.init()) return e;
@@ -383,7 +391,7 @@ static int run_host_pipeline(mdc_handle_s* h, const In* x, int64_t n, O0* o0, O1
   }
   if (hist) MDC_CUDA(cudaMemsetAsync(P.hist.ptr, 0, C * sizeof(unsigned long long), P.s_comp));
   for (int k = 0; k < S; ++k) {
-    if (int e = P.x[k].reserve((size_t)chunk * kFrameElems * sizeof(In))) return e;
+    if (int e = P.x[k].reserve((size_t)chunk * fb)) return e;
     if (o0) if (int e = P.o0[k].reserve((size_t)chunk * C * sizeof(O0))) return e;
     if (o1) if (int e = P.o1[k].reserve((size_t)chunk * C * sizeof(O1))) return e;
     if (cls) if (int e = P.o2[k].reserve((size_t)chunk * sizeof(int32_t))) return e;
@@ -393,10 +401,10 @@ static int run_host_pipeline(mdc_handle_s* h, const In* x, int64_t n, O0* o0, O1
     const int k = (int)(i % S);
     const int64_t m = (n - s) < chunk ? (n - s) : chunk;
     MDC_CUDA(cudaStreamWaitEvent(P.s_h2d, P.e_comp[k], 0));        // (a never-recorded event does not block)
-    if (int e = h2d_chunk(P, k, P.x[k].ptr, x + s * kFrameElems, (size_t)m * kFrameElems * sizeof(In), pageable)) return e;
+    if (int e = h2d_chunk(P, k, P.x[k].ptr, x + (size_t)s * fb, (size_t)m * fb, pageable)) return e;
     MDC_CUDA(cudaStreamWaitEvent(P.s_comp, P.e_h2d[k], 0));
     MDC_CUDA(cudaStreamWaitEvent(P.s_comp, P.e_d2h[k], 0));
-    if (int e = launch((const In*)P.x[k].ptr, m, o0 ? (O0*)P.o0[k].ptr : nullptr,
+    if (int e = launch((const void*)P.x[k].ptr, m, o0 ? (O0*)P.o0[k].ptr : nullptr,
                        o1 ? (O1*)P.o1[k].ptr : nullptr, cls ? (int32_t*)P.o2[k].ptr : nullptr,
                        hist ? (unsigned long long*)P.hist.ptr : nullptr, P.s_comp))
       return e;
@@ -712,15 +720,21 @@ int mdc_range_flags(mdc_handle_t h, unsigned int* flags, int reset) {
   return MDC_OK;
 }
 
-int mdc_predict_q612(mdc_handle_t h, const int32_t* x_dev, int64_t n, int32_t* out_dev, int32_t* pre_dev,
-                     int32_t* cls_dev, unsigned long long* hist_dev, void* stream) {
+int mdc_predict_q612_raw(mdc_handle_t h, const void* x_dev, int in_format, int64_t n, int32_t* out_dev, int32_t* pre_dev,
+                         int32_t* cls_dev, unsigned long long* hist_dev, void* stream) {
   MDC_CHECK_HANDLE(h);
   MDC_REQUIRE(h->mode == MDC_MODE_Q612, MDC_ERR_INVALID, "handle is not in Q6.12 mode");
   MDC_REQUIRE(h->have_q, MDC_ERR_NOT_READY, "ROM tables not set (call mdc_set_weights_q612)");
   MDC_REQUIRE(n >= 0, MDC_ERR_INVALID, "n=%lld < 0", (long long)n);
   MDC_REQUIRE(n == 0 || x_dev != nullptr, MDC_ERR_INVALID, "x_dev is NULL");
   MDC_REQUIRE(((uintptr_t)x_dev & 15) == 0, MDC_ERR_INVALID, "x_dev must be 16-byte aligned");
-  return launch_q612(h, x_dev, n, out_dev, pre_dev, cls_dev, hist_dev, (cudaStream_t)stream);
+  if (int e = check_q612_format(in_format)) return e;
+  return launch_q612(h, x_dev, in_format, n, out_dev, pre_dev, cls_dev, hist_dev, (cudaStream_t)stream);
+}
+
+int mdc_predict_q612(mdc_handle_t h, const int32_t* x_dev, int64_t n, int32_t* out_dev, int32_t* pre_dev,
+                     int32_t* cls_dev, unsigned long long* hist_dev, void* stream) {
+  return mdc_predict_q612_raw(h, x_dev, MDC_IN_I32, n, out_dev, pre_dev, cls_dev, hist_dev, stream);
 }
 
 static int predict_f32_host_impl(mdc_handle_t h, const void* x_host, int in_fmt, int64_t n, float* probs_host,
@@ -736,29 +750,32 @@ static int predict_f32_host_impl(mdc_handle_t h, const void* x_host, int in_fmt,
   }
   if (vt_tensor_mode(h))
     return run_vt_host_pipeline(h, x_host, in_fmt, n, probs_host, dense_host, cls_host, hist_host, ticket);
-  const int64_t chunk = 16384;
-  return run_host_pipeline<float, float, float>(
-      h, (const float*)x_host, n, probs_host, dense_host, cls_host, hist_host, chunk, ticket,
-      [h](const float* x, int64_t m, float* p, float* d, int32_t* c, unsigned long long* hs, cudaStream_t s) {
-        return predict_f32_dev(h, x, MDC_IN_F32, m, p, d, c, hs, s);
+  // 16 MiB of frames per chunk whatever the format (a narrow format would otherwise mean 4 MiB copies and four
+  // times the launches per byte)
+  const int64_t chunk = (int64_t)16384 * (1024 / (int64_t)frame_bytes(in_fmt));
+  return run_host_pipeline<float, float>(
+      h, x_host, frame_bytes(in_fmt), n, probs_host, dense_host, cls_host, hist_host, chunk, ticket,
+      [h, in_fmt](const void* x, int64_t m, float* p, float* d, int32_t* c, unsigned long long* hs, cudaStream_t s) {
+        return predict_f32_dev(h, x, in_fmt, m, p, d, c, hs, s);
       });
 }
 
-static int predict_q612_host_impl(mdc_handle_t h, const int32_t* x_host, int64_t n, int32_t* out_host, int32_t* pre_host,
-                                  int32_t* cls_host, unsigned long long* hist_host, int64_t* ticket) {
+static int predict_q612_host_impl(mdc_handle_t h, const void* x_host, int in_fmt, int64_t n, int32_t* out_host,
+                                  int32_t* pre_host, int32_t* cls_host, unsigned long long* hist_host, int64_t* ticket) {
   MDC_CHECK_HANDLE(h);
   MDC_REQUIRE(h->mode == MDC_MODE_Q612, MDC_ERR_INVALID, "handle is not in Q6.12 mode");
   MDC_REQUIRE(h->have_q, MDC_ERR_NOT_READY, "ROM tables not set (call mdc_set_weights_q612)");
   MDC_REQUIRE(n >= 0 && (n == 0 || x_host), MDC_ERR_INVALID, "bad x_host / n");
+  if (int e = check_q612_format(in_fmt)) return e;
   if (n == 0) {
     if (hist_host) memset(hist_host, 0, h->C * sizeof(unsigned long long));
     return MDC_OK;
   }
-  const int64_t chunk = 16384;
-  return run_host_pipeline<int32_t, int32_t, int32_t>(
-      h, x_host, n, out_host, pre_host, cls_host, hist_host, chunk, ticket,
-      [h](const int32_t* x, int64_t m, int32_t* o, int32_t* p, int32_t* c, unsigned long long* hs, cudaStream_t s) {
-        return launch_q612(h, x, m, o, p, c, hs, s);
+  const int64_t chunk = (int64_t)16384 * (1024 / (int64_t)frame_bytes(in_fmt));   // 16 MiB of frames per chunk
+  return run_host_pipeline<int32_t, int32_t>(
+      h, x_host, frame_bytes(in_fmt), n, out_host, pre_host, cls_host, hist_host, chunk, ticket,
+      [h, in_fmt](const void* x, int64_t m, int32_t* o, int32_t* p, int32_t* c, unsigned long long* hs, cudaStream_t s) {
+        return launch_q612(h, x, in_fmt, m, o, p, c, hs, s);
       });
 }
 
@@ -786,11 +803,16 @@ int mdc_predict_raw_host_async(mdc_handle_t h, const void* x_host, int in_format
   return predict_f32_host_impl(h, x_host, in_format, n, probs_host, dense_host, cls_host, hist_host, ticket);
 }
 
-int mdc_predict_q612_host_async(mdc_handle_t h, const int32_t* x_host, int64_t n, int32_t* out_host, int32_t* pre_host,
-                                int32_t* cls_host, unsigned long long* hist_host, int64_t* ticket) {
+int mdc_predict_q612_raw_host_async(mdc_handle_t h, const void* x_host, int in_format, int64_t n, int32_t* out_host,
+                                    int32_t* pre_host, int32_t* cls_host, unsigned long long* hist_host, int64_t* ticket) {
   MDC_REQUIRE(ticket != nullptr, MDC_ERR_INVALID, "ticket is NULL");
   *ticket = 0;
-  return predict_q612_host_impl(h, x_host, n, out_host, pre_host, cls_host, hist_host, ticket);
+  return predict_q612_host_impl(h, x_host, in_format, n, out_host, pre_host, cls_host, hist_host, ticket);
+}
+
+int mdc_predict_q612_host_async(mdc_handle_t h, const int32_t* x_host, int64_t n, int32_t* out_host, int32_t* pre_host,
+                                int32_t* cls_host, unsigned long long* hist_host, int64_t* ticket) {
+  return mdc_predict_q612_raw_host_async(h, x_host, MDC_IN_I32, n, out_host, pre_host, cls_host, hist_host, ticket);
 }
 
 int mdc_host_wait(mdc_handle_t h, int64_t ticket) {
@@ -806,9 +828,14 @@ int mdc_host_wait(mdc_handle_t h, int64_t ticket) {
   return MDC_OK;
 }
 
+int mdc_predict_q612_raw_host(mdc_handle_t h, const void* x_host, int in_format, int64_t n, int32_t* out_host,
+                              int32_t* pre_host, int32_t* cls_host, unsigned long long* hist_host) {
+  return predict_q612_host_impl(h, x_host, in_format, n, out_host, pre_host, cls_host, hist_host, nullptr);
+}
+
 int mdc_predict_q612_host(mdc_handle_t h, const int32_t* x_host, int64_t n, int32_t* out_host, int32_t* pre_host,
                           int32_t* cls_host, unsigned long long* hist_host) {
-  return predict_q612_host_impl(h, x_host, n, out_host, pre_host, cls_host, hist_host, nullptr);
+  return predict_q612_host_impl(h, x_host, MDC_IN_I32, n, out_host, pre_host, cls_host, hist_host, nullptr);
 }
 
 // ---- FWHT ------------------------------------------------------------------------------

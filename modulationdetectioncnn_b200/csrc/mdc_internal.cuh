@@ -104,9 +104,11 @@ struct mdc_handle_s {
 namespace mdc {
 
 // kernels' launchers: all enqueue on `stream`, bump h->launches
-int launch_q612(mdc_handle_s* h, const int32_t* x, int64_t n, int32_t* out, int32_t* pre,
+// x holds frames in format in_fmt: MDC_IN_I32 (the 18-bit words of test_table), MDC_IN_I16 or MDC_IN_U8IQ
+int launch_q612(mdc_handle_s* h, const void* x, int in_fmt, int64_t n, int32_t* out, int32_t* pre,
                 int32_t* cls, unsigned long long* hist, cudaStream_t stream);
-int launch_tiny_f32(mdc_handle_s* h, const float* x, int64_t n, float* probs, float* dense,
+// x holds frames in format in_fmt (MDC_IN_*; the raw formats need one of the specialised shapes)
+int launch_tiny_f32(mdc_handle_s* h, const void* x, int in_fmt, int64_t n, float* probs, float* dense,
                     int32_t* cls, unsigned long long* hist, cudaStream_t stream);
 int launch_vt_f32(mdc_handle_s* h, const float* x, int64_t n, float* probs, float* dense,
                   int32_t* cls, unsigned long long* hist, cudaStream_t stream);

@@ -156,11 +156,64 @@ __device__ __forceinline__ void q612_frame(const QParams& p, const int4* __restr
   cnt += (lane == best);
 }
 
+// A lane's eight samples of one frame as they sit in global memory, per frame format:
+//   MDC_IN_I32   int32 [256] (0-127 I, 128-255 Q; the 18-bit words of test_table, sv:88-102): two 16-B loads
+//   MDC_IN_I16   int16 [256], same address map (Q6.12 fits 16 bits up to +-8.0):              two 8-B loads
+//   MDC_IN_U8IQ  u8 [128][2], raw RTL-SDR bytes I0 Q0 I1 Q1 ...; Q6.12 value (2u - 255) * 16  one 8-B load
+//                (exactly (u - 127.5) / 128, as mdc_sdr_ingest_u8 writes it)
+template <int FMT>
+struct QRaw {
+  int4 a, b;
+};
+template <>
+struct QRaw<MDC_IN_I16> {
+  uint2 a, b;
+};
+template <>
+struct QRaw<MDC_IN_U8IQ> {
+  uint2 a;
+};
+__device__ __forceinline__ uint2 ldg_stream8(const void* p) {
+  uint2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+  return r;
+}
+template <int FMT>
+__device__ __forceinline__ QRaw<FMT> q_load(const uint8_t* x, unsigned f, int lane) {
+  QRaw<FMT> r;
+  if constexpr (FMT == MDC_IN_I32) {
+    const int4* p = reinterpret_cast<const int4*>(x) + (size_t)f * 64 + lane;
+    r.a = ldg_stream(p);
+    r.b = ldg_stream(p + 32);
+  } else if constexpr (FMT == MDC_IN_I16) {
+    const uint8_t* p = x + (size_t)f * 512 + 8 * lane;
+    r.a = ldg_stream8(p);
+    r.b = ldg_stream8(p + 256);
+  } else {
+    r.a = ldg_stream8(x + (size_t)f * 256 + 8 * lane);
+  }
+  return r;
+}
+template <int FMT>
+__device__ __forceinline__ void q_unpack(const QRaw<FMT>& r, int4& xi, int4& xq) {
+  if constexpr (FMT == MDC_IN_I32) {
+    xi = r.a;
+    xq = r.b;
+  } else if constexpr (FMT == MDC_IN_I16) {
+    xi = make_int4((short)(r.a.x & 0xFFFFu), (int)r.a.x >> 16, (short)(r.a.y & 0xFFFFu), (int)r.a.y >> 16);
+    xq = make_int4((short)(r.b.x & 0xFFFFu), (int)r.b.x >> 16, (short)(r.b.y & 0xFFFFu), (int)r.b.y >> 16);
+  } else {
+    auto cv = [](unsigned u) { return 32 * (int)u - 4080; };
+    xi = make_int4(cv(r.a.x & 255u), cv((r.a.x >> 16) & 255u), cv(r.a.y & 255u), cv((r.a.y >> 16) & 255u));
+    xq = make_int4(cv((r.a.x >> 8) & 255u), cv(r.a.x >> 24), cv((r.a.y >> 8) & 255u), cv(r.a.y >> 24));
+  }
+}
+
 // dense image: [f][c][iq][128] with entry s = tab[2c+iq][128 f + max(s-1,0)]  (pre-skewed on host)
 // n * C < 2^32 (launch_q612 splits longer batches): frame and output indices are 32-bit.
-template <int F, int C, int MINB>
+template <int F, int C, int MINB, int FMT>
 __global__ void __launch_bounds__(256, MINB)
-q612_kernel(const QParams p, const int4* __restrict__ dense4, const int4* __restrict__ x,
+q612_kernel(const QParams p, const int4* __restrict__ dense4, const uint8_t* __restrict__ x,
             unsigned n, int* __restrict__ out, int* __restrict__ pre, int* __restrict__ cls,
             unsigned long long* __restrict__ hist) {
   const int lane = threadIdx.x & 31;
@@ -170,28 +223,25 @@ q612_kernel(const QParams p, const int4* __restrict__ dense4, const int4* __rest
   unsigned cnt = 0;
 
   unsigned f = warp;
-  int4 xi, xq;
-  if (f < n) {
-    xi = ldg_stream(x + (size_t)f * 64 + lane);
-    xq = ldg_stream(x + (size_t)f * 64 + 32 + lane);
-  }
+  QRaw<FMT> cur;
+  if (f < n) cur = q_load<FMT>(x, f, lane);
   while (f < n) {
     const unsigned fn = f + nwarps;
-    int4 ni = xi, nq = xq;
-    if (fn < n) {  // prefetch the next frame of this warp
-      ni = ldg_stream(x + (size_t)fn * 64 + lane);
-      nq = ldg_stream(x + (size_t)fn * 64 + 32 + lane);
-    }
+    QRaw<FMT> nxt = cur;
+    if (fn < n) nxt = q_load<FMT>(x, fn, lane);   // prefetch the next frame of this warp
+    int4 xi, xq;
+    q_unpack<FMT>(cur, xi, xq);
     q612_frame<F, C>(p, dense4, xi, xq, lane, f, wmask, out, pre, cls, cnt);
-    xi = ni; xq = nq;
+    cur = nxt;
     f = fn;
   }
   if (hist && lane < C && cnt) atomicAdd(hist + lane, (unsigned long long)cnt);
 }
 
 // Any F<=16, C<=16: runtime loops, ROM entries read through L1.
+template <int FMT>
 __global__ void __launch_bounds__(256)
-q612_generic_kernel(const QParams p, const int4* __restrict__ dense4, const int4* __restrict__ x,
+q612_generic_kernel(const QParams p, const int4* __restrict__ dense4, const uint8_t* __restrict__ x,
                     long long n, int* __restrict__ out, int* __restrict__ pre,
                     int* __restrict__ cls, unsigned long long* __restrict__ hist) {
   const int lane = threadIdx.x & 31;
@@ -200,7 +250,8 @@ q612_generic_kernel(const QParams p, const int4* __restrict__ dense4, const int4
   const int F = p.F, C = p.C;
   unsigned cnt = 0;
   for (long long f = warp; f < n; f += nwarps) {
-    int4 xi = ldg_stream(x + f * 64 + lane), xq = ldg_stream(x + f * 64 + 32 + lane);
+    int4 xi, xq;
+    q_unpack<FMT>(q_load<FMT>(x, (unsigned)f, lane), xi, xq);
     int I[5], Q[5];
     I[1] = wrap18(xi.x); I[2] = wrap18(xi.y); I[3] = wrap18(xi.z); I[4] = wrap18(xi.w);
     Q[1] = wrap18(xq.x); Q[2] = wrap18(xq.y); Q[3] = wrap18(xq.z); Q[4] = wrap18(xq.w);
@@ -247,7 +298,20 @@ q612_generic_kernel(const QParams p, const int4* __restrict__ dense4, const int4
   if (hist && lane < C && cnt) atomicAdd(hist + lane, (unsigned long long)cnt);
 }
 
-int launch_q612(mdc_handle_s* h, const int32_t* x, int64_t n, int32_t* out, int32_t* pre,
+template <int FMT>
+static void q612_dispatch(const mdc_handle_s* h, const QParams& p, unsigned blocks, int threads, cudaStream_t stream,
+                          const int4* d4, const uint8_t* xb, unsigned m, int* o, int* pr, int* cl, unsigned long long* hist) {
+  if (h->F == 3 && h->C == 3) {
+    q612_kernel<3, 3, 4, FMT><<<blocks, threads, 0, stream>>>(p, d4, xb, m, o, pr, cl, hist);
+  } else if (h->F == 10 && h->C == 3) {
+    // the 10-filter model (DenseWeights1.txt)
+    q612_kernel<10, 3, 4, FMT><<<blocks, threads, 0, stream>>>(p, d4, xb, m, o, pr, cl, hist);
+  } else {
+    q612_generic_kernel<FMT><<<blocks, threads, 0, stream>>>(p, d4, xb, (long long)m, o, pr, cl, hist);
+  }
+}
+
+int launch_q612(mdc_handle_s* h, const void* x, int in_fmt, int64_t n, int32_t* out, int32_t* pre,
                 int32_t* cls, unsigned long long* hist, cudaStream_t stream) {
   if (n == 0) return MDC_OK;
   QParams p;
@@ -269,18 +333,14 @@ int launch_q612(mdc_handle_s* h, const int32_t* x, int64_t n, int32_t* out, int3
   const long long piece = (1ll << 32) / kMaxClasses - 1;     // frame and output indices are 32-bit inside the kernels
   for (long long done = 0; done < n; done += piece) {
     const unsigned m = (unsigned)std::min(piece, n - done);
-    const int4* x4 = reinterpret_cast<const int4*>(x + done * kFrameElems);
+    const size_t fb = in_fmt == MDC_IN_U8IQ ? 256 : (in_fmt == MDC_IN_I16 ? 512 : 1024);
+    const uint8_t* xb = reinterpret_cast<const uint8_t*>(x) + (size_t)done * fb;
     int* o = out ? out + done * h->C : nullptr;
     int* pr = pre ? pre + done * h->C : nullptr;
     int* cl = cls ? cls + done : nullptr;
-    if (h->F == 3 && h->C == 3) {
-      q612_kernel<3, 3, 4><<<(unsigned)blocks, threads, 0, stream>>>(p, d4, x4, m, o, pr, cl, hist);
-    } else if (h->F == 10 && h->C == 3) {
-      // the 10-filter model (DenseWeights1.txt)
-      q612_kernel<10, 3, 4><<<(unsigned)blocks, threads, 0, stream>>>(p, d4, x4, m, o, pr, cl, hist);
-    } else {
-      q612_generic_kernel<<<(unsigned)blocks, threads, 0, stream>>>(p, d4, x4, (long long)m, o, pr, cl, hist);
-    }
+    if (in_fmt == MDC_IN_U8IQ) q612_dispatch<MDC_IN_U8IQ>(h, p, (unsigned)blocks, threads, stream, d4, xb, m, o, pr, cl, hist);
+    else if (in_fmt == MDC_IN_I16) q612_dispatch<MDC_IN_I16>(h, p, (unsigned)blocks, threads, stream, d4, xb, m, o, pr, cl, hist);
+    else q612_dispatch<MDC_IN_I32>(h, p, (unsigned)blocks, threads, stream, d4, xb, m, o, pr, cl, hist);
   }
   prof_end(h, stream);
   h->launches++;

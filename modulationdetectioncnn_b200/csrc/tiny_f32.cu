@@ -58,30 +58,71 @@ struct TinyParams4 {
   float zero;                                                            // 0.0f (see the shifted pairs in the kernel)
 };
 
-template <int F, int C, int W, int B>
+// FMT: frame format in global memory and in the ring (MDC_IN_F32 1,024 B, MDC_IN_U8IQ 256 B, MDC_IN_I16 512 B per
+// frame); raw formats are converted when a lane picks its samples out of the ring - exact, so the results are
+// bit-identical to mdc_sdr_ingest_u8 (or s / 4096) followed by the f32 call.
+template <int F, int C, int W, int B, int FMT = MDC_IN_F32>
 struct Tiny4 {
   static constexpr int kWarps = W, kThreads = kWarps * 32, R = 4, kBufs = B;
+  static constexpr int kFB = FMT == MDC_IN_U8IQ ? 256 : (FMT == MDC_IN_I16 ? 512 : 1024);   // bytes per frame
   static constexpr int kWBytes = 2 * F * C * 128 * 4;
   static constexpr int ring = kWBytes;
-  static constexpr int bars = ring + kWarps * kBufs * R * 1024;
+  static constexpr int bars = ring + kWarps * kBufs * R * kFB;
   static constexpr int total = bars + kWarps * kBufs * 8;
   static_assert(C <= 4 && 2 * F <= 32, "shape outside the specialisation");
 };
 
-template <int F, int C, int W, int B>
-__global__ void __launch_bounds__(Tiny4<F, C, W, B>::kThreads, 1)
+// the lane's samples of one staged frame: positions 4 lane .. 4 lane + 3 of both rows, and the sample left of them
+template <int FMT>
+__device__ __forceinline__ void tiny_lane_samples(const uint8_t* fr, int lane, float4& xi, float4& xq, float& pi, float& pq) {
+  if constexpr (FMT == MDC_IN_F32) {
+    const float* f = reinterpret_cast<const float*>(fr);
+    xi = reinterpret_cast<const float4*>(f)[lane];
+    xq = reinterpret_cast<const float4*>(f + 128)[lane];
+    pi = lane ? f[4 * lane - 1] : 0.f;
+    pq = lane ? f[128 + 4 * lane - 1] : 0.f;
+  } else if constexpr (FMT == MDC_IN_U8IQ) {
+    // I0 Q0 I1 Q1 ...: value (u - 127.5) / 128 = (2u - 255) / 256, exact (== sdr_ingest_kernel)
+    auto cv = [](unsigned u) { return (float)(2 * (int)u - 255) * (1.f / 256.f); };
+    const uint2 b = reinterpret_cast<const uint2*>(fr)[lane];
+    xi = make_float4(cv(b.x & 255u), cv((b.x >> 16) & 255u), cv(b.y & 255u), cv((b.y >> 16) & 255u));
+    xq = make_float4(cv((b.x >> 8) & 255u), cv(b.x >> 24), cv((b.y >> 8) & 255u), cv(b.y >> 24));
+    const unsigned pb = lane ? reinterpret_cast<const uint16_t*>(fr)[4 * lane - 1] : 0u;
+    pi = lane ? cv(pb & 255u) : 0.f;
+    pq = lane ? cv(pb >> 8) : 0.f;
+  } else {
+    // int16 [2][128] Q6.12 in the test_table address map: value s / 4096, exact
+    const int16_t* h = reinterpret_cast<const int16_t*>(fr);
+    auto cv = [](int v) { return (float)v * (1.f / 4096.f); };
+    const uint2 a = reinterpret_cast<const uint2*>(h)[lane], b = reinterpret_cast<const uint2*>(h + 128)[lane];
+    xi = make_float4(cv((short)(a.x & 0xFFFFu)), cv((int)a.x >> 16), cv((short)(a.y & 0xFFFFu)), cv((int)a.y >> 16));
+    xq = make_float4(cv((short)(b.x & 0xFFFFu)), cv((int)b.x >> 16), cv((short)(b.y & 0xFFFFu)), cv((int)b.y >> 16));
+    pi = lane ? cv(h[4 * lane - 1]) : 0.f;
+    pq = lane ? cv(h[128 + 4 * lane - 1]) : 0.f;
+  }
+}
+// sample 127 of row r (position 128 of the padded row only needs that one)
+template <int FMT>
+__device__ __forceinline__ float tiny_last_sample(const uint8_t* fr, int r) {
+  if constexpr (FMT == MDC_IN_F32) return reinterpret_cast<const float*>(fr)[r * 128 + 127];
+  else if constexpr (FMT == MDC_IN_U8IQ) return (float)(2 * (int)fr[254 + r] - 255) * (1.f / 256.f);
+  else return (float)reinterpret_cast<const int16_t*>(fr)[r * 128 + 127] * (1.f / 4096.f);
+}
+
+template <int F, int C, int W, int B, int FMT>
+__global__ void __launch_bounds__(Tiny4<F, C, W, B, FMT>::kThreads, 1)
 tiny_f32_kernel4(const __grid_constant__ TinyParams4 p, const float4* __restrict__ dmain, const float* __restrict__ dtail,
-                 const float* __restrict__ x, long long n, float* __restrict__ probs, float* __restrict__ dense,
+                 const uint8_t* __restrict__ x, long long n, float* __restrict__ probs, float* __restrict__ dense,
                  int* __restrict__ cls, unsigned long long* __restrict__ hist) {
-  using Cfg = Tiny4<F, C, W, B>;
-  constexpr int R = Cfg::R, kBufs = Cfg::kBufs;
+  using Cfg = Tiny4<F, C, W, B, FMT>;
+  constexpr int R = Cfg::R, kBufs = Cfg::kBufs, kFB = Cfg::kFB;
   extern __shared__ __align__(128) uint8_t smem[];
   // let the next launch on the stream start its own prologue (weight image to shared memory, barriers) on SMs as this
   // grid's CTAs retire: back-to-back launches of 65,536 frames last 20-40 us, a 5 us gap + prologue is 15-25 % of that
   asm volatile("griddepcontrol.launch_dependents;");
   const float4* wsm = reinterpret_cast<const float4*>(smem);
   const int lane = threadIdx.x & 31, warp = uniform_warp_idx();
-  uint8_t* myring = smem + Cfg::ring + warp * (kBufs * R * 1024);
+  uint8_t* myring = smem + Cfg::ring + warp * (kBufs * R * kFB);
   uint64_t* mybar = reinterpret_cast<uint64_t*>(smem + Cfg::bars) + warp * kBufs;
 
   {
@@ -115,9 +156,9 @@ tiny_f32_kernel4(const __grid_constant__ TinyParams4 p, const float4* __restrict
   auto issue = [&](long long grp, int b) {        // this warp's frames of group grp -> buffer b
     if (grp < ngroups && elect_one()) {
       const long long f0 = grp * R, left = n - f0;
-      const uint32_t bytes = (uint32_t)(left < R ? left : R) * 1024u;
+      const uint32_t bytes = (uint32_t)(left < R ? left : R) * (uint32_t)kFB;
       mbar_arrive_expect_tx(&mybar[b], bytes);
-      bulk_g2s(myring + b * (R * 1024), x + f0 * 256, bytes, &mybar[b]);
+      bulk_g2s(myring + b * (R * kFB), x + f0 * kFB, bytes, &mybar[b]);
     }
     __syncwarp();
   };
@@ -133,17 +174,16 @@ tiny_f32_kernel4(const __grid_constant__ TinyParams4 p, const float4* __restrict
     // the buffer read in the previous pass is free: every value loaded from it has been consumed by then
     issue(g + (kBufs - 1) * stride, (it + kBufs - 1) % kBufs);
     mbar_wait(&mybar[b], (it / kBufs) & 1);
-    const float* fr = reinterpret_cast<const float*>(myring + b * (R * 1024));
+    const uint8_t* fr = myring + b * (R * kFB);
     const long long f0 = g * R;
 
     uint64_t acc[R][C];       // {even positions, odd positions} partial sums
     uint64_t PI01[R], PI23[R], XI01[R], XI23[R], PQ01[R], PQ23[R], XQ01[R], XQ23[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      const float4 xi = reinterpret_cast<const float4*>(fr + r * 256)[lane];
-      const float4 xq = reinterpret_cast<const float4*>(fr + r * 256 + 128)[lane];
-      const float pi = lane ? fr[r * 256 + 4 * lane - 1] : 0.f;
-      const float pq = lane ? fr[r * 256 + 128 + 4 * lane - 1] : 0.f;
+      float4 xi, xq;
+      float pi, pq;
+      tiny_lane_samples<FMT>(fr + r * kFB, lane, xi, xq, pi, pq);
       // y[i] = relu(x[i-1] k0 + x[i] k1 + b): pairs (y0,y1) and (y2,y3)
       // The shifted pairs (x[4l-1], x[4l]) and (x[4l+1], x[4l+2]) straddle the register pairs the 16-B loads fill.
       // Built with plain moves, ptxas re-copies them next to every use (170 MOVs per pass for F = 10); an add of a
@@ -199,7 +239,7 @@ tiny_f32_kernel4(const __grid_constant__ TinyParams4 p, const float4* __restrict
     // position 128: xp[128] = x[127], xp[129] = 0 (the frames are still in this pass's buffer)
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-      const float yt = fmaxf(fmaf(fr[r * 256 + (lane < 2 * F ? tr : 0) * 128 + 127], tk0, tb), 0.f);
+      const float yt = fmaxf(fmaf(tiny_last_sample<FMT>(fr + r * kFB, lane < 2 * F ? tr : 0), tk0, tb), 0.f);
 #pragma unroll
       for (int c = 0; c < C; ++c) v[r * 4 + c] = fmaf(yt, tw[c], v[r * 4 + c]);   // tw = 0 in lanes without a (row, filter)
     }
@@ -353,9 +393,14 @@ int pack_tiny(mdc_handle_s* h) {
   return MDC_OK;
 }
 
-int launch_tiny_f32(mdc_handle_s* h, const float* x, int64_t n, float* probs, float* dense,
+int launch_tiny_f32(mdc_handle_s* h, const void* xv, int in_fmt, int64_t n, float* probs, float* dense,
                     int32_t* cls, unsigned long long* hist, cudaStream_t stream) {
   if (n == 0) return MDC_OK;
+  const float* x = reinterpret_cast<const float*>(xv);
+  const uint8_t* xb = reinterpret_cast<const uint8_t*>(xv);
+  const bool special = (h->F == 3 || h->F == 10) && h->C == 3;
+  MDC_REQUIRE(in_fmt == MDC_IN_F32 || special, MDC_ERR_UNSUPPORTED,
+              "raw u8 / int16 frames: TinyCNN2 shapes F in {3, 10}, C = 3 only (this handle: F=%d, C=%d)", h->F, h->C);
   TinyParams p;
   const int F = h->F, C = h->C;
   const float* K = h->w[MDC_T_CONV1_K].data();   // (1,2,1,F): [tap][f]
@@ -378,12 +423,12 @@ int launch_tiny_f32(mdc_handle_s* h, const float* x, int64_t n, float* probs, fl
     long long max_blocks = (long long)h->num_sms * 2 * 4;
     return (unsigned)(blocks > max_blocks ? max_blocks : blocks);
   };
-#define MDC_TINY4_LAUNCH(F_, C_, W_, B_)                                                                      \
+#define MDC_TINY4_LAUNCH(F_, C_, W_, B_, FMT_)                                                                \
   do {                                                                                                        \
-    using Cfg_ = Tiny4<F_, C_, W_, B_>;                                                                       \
+    using Cfg_ = Tiny4<F_, C_, W_, B_, FMT_>;                                                                 \
     static bool attr_ = false;                                                                                \
     if (!attr_) {                                                                                             \
-      MDC_CUDA(cudaFuncSetAttribute(tiny_f32_kernel4<F_, C_, W_, B_>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg_::total)); \
+      MDC_CUDA(cudaFuncSetAttribute(tiny_f32_kernel4<F_, C_, W_, B_, FMT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg_::total)); \
       attr_ = true;                                                                                           \
     }                                                                                                         \
     const long long ngroups_ = (n + Cfg_::R - 1) / Cfg_::R;                                                   \
@@ -399,7 +444,7 @@ int launch_tiny_f32(mdc_handle_s* h, const float* x, int64_t n, float* probs, fl
     pdl_[0].val.programmaticStreamSerializationAllowed = 1;                                                   \
     cfg_.attrs = pdl_;                                                                                        \
     cfg_.numAttrs = 1;                                                                                        \
-    MDC_CUDA(cudaLaunchKernelEx(&cfg_, tiny_f32_kernel4<F_, C_, W_, B_>, p4, dm, dt, x, (long long)n, probs, dense, cls, hist)); \
+    MDC_CUDA(cudaLaunchKernelEx(&cfg_, tiny_f32_kernel4<F_, C_, W_, B_, FMT_>, p4, dm, dt, xb, (long long)n, probs, dense, cls, hist)); \
   } while (0)
   TinyParams4 p4;
   for (int f = 0; f < kMaxFilters; ++f) {
@@ -417,10 +462,16 @@ int launch_tiny_f32(mdc_handle_s* h, const float* x, int64_t n, float* probs, fl
   prof_begin(h, stream);
   // 16 warps x 3 buffers: measured against 14 warps (F = 10: 1.60e9 -> 1.84e9 frames/s - the kernel wants warps to
   // fill the FMA pipe's off-cycles); 18+ warps would leave < 128 registers per thread and spill
+#define MDC_TINY4_FORMATS(F_)                                                 \
+  do {                                                                         \
+    if (in_fmt == MDC_IN_U8IQ) MDC_TINY4_LAUNCH(F_, 3, 16, 3, MDC_IN_U8IQ);    \
+    else if (in_fmt == MDC_IN_I16) MDC_TINY4_LAUNCH(F_, 3, 16, 3, MDC_IN_I16); \
+    else MDC_TINY4_LAUNCH(F_, 3, 16, 3, MDC_IN_F32);                           \
+  } while (0)
   if (F == 3 && C == 3) {
-    MDC_TINY4_LAUNCH(3, 3, 16, 3);
+    MDC_TINY4_FORMATS(3);
   } else if (F == 10 && C == 3) {
-    MDC_TINY4_LAUNCH(10, 3, 16, 3);
+    MDC_TINY4_FORMATS(10);
   } else {
     tiny_f32_generic_kernel<<<grid(1), threads, 0, stream>>>(
         p, reinterpret_cast<const float*>(h->tiny_dense.ptr), dt, x4, n, probs, dense, cls, hist);

@@ -17,6 +17,18 @@ from .svtext import QWeights
 __all__ = ["FixedPointCNN2"]
 
 
+def _host_frames(x):
+    """(array [N, row bytes], MDC_IN_* format) for a host batch: uint8 -> raw interleaved I/Q bytes [N,128,2]
+    (sample = (2u - 255) * 16, what sdr.ingest_u8 writes); int16 -> Q6.12 samples [N,256]; anything else -> the int32
+    words of test_table [N,256]."""
+    a = np.asarray(x)
+    if a.dtype == np.uint8:
+        return np.ascontiguousarray(a).reshape(-1, 256), _lib.IN_U8IQ
+    if a.dtype == np.int16:
+        return np.ascontiguousarray(a).reshape(-1, 256), _lib.IN_I16
+    return np.ascontiguousarray(a, dtype=np.int32).reshape(-1, 256), _lib.IN_I32
+
+
 def _is_torch(x) -> bool:
     return type(x).__module__.split(".")[0] == "torch"
 
@@ -55,7 +67,12 @@ class FixedPointCNN2:
                 raise ValueError("torch inputs must be CUDA tensors (pass numpy for the host path)")
             if x.device.index != self.device:
                 raise ValueError(f"input lives on cuda:{x.device.index}, this model on cuda:{self.device}")
-            xt = x.reshape(-1, 256).to(torch.int32).contiguous()
+            if x.dtype == torch.uint8:
+                xt, fmt = x.reshape(-1, 256).contiguous(), _lib.IN_U8IQ
+            elif x.dtype == torch.int16:
+                xt, fmt = x.reshape(-1, 256).contiguous(), _lib.IN_I16
+            else:
+                xt, fmt = x.reshape(-1, 256).to(torch.int32).contiguous(), _lib.IN_I32
             n = xt.shape[0]
             out: Dict[str, object] = {}
             with torch.cuda.device(xt.device):
@@ -67,10 +84,10 @@ class FixedPointCNN2:
                     else:
                         out[k] = torch.empty((n, Cn), dtype=torch.int32, device=xt.device)
                 ptr = lambda k: out[k].data_ptr() if k in out else None  # noqa: E731
-                _lib.check(lib.mdc_predict_q612(self._h.ptr, xt.data_ptr(), n, ptr("out"), ptr("pre"), ptr("cls"),
-                                                ptr("hist"), torch.cuda.current_stream(xt.device).cuda_stream))
+                _lib.check(lib.mdc_predict_q612_raw(self._h.ptr, xt.data_ptr(), fmt, n, ptr("out"), ptr("pre"), ptr("cls"),
+                                                    ptr("hist"), torch.cuda.current_stream(xt.device).cuda_stream))
             return out
-        xa = np.ascontiguousarray(x, dtype=np.int32).reshape(-1, 256)
+        xa, fmt = _host_frames(x)
         n = xa.shape[0]
         out = {}
         for k in want:
@@ -81,15 +98,16 @@ class FixedPointCNN2:
             else:
                 out[k] = np.empty((n, Cn), dtype=np.int32)
         ptr = lambda k: out[k].ctypes.data if k in out else None  # noqa: E731
-        _lib.check(lib.mdc_predict_q612_host(self._h.ptr, xa.ctypes.data, n, ptr("out"), ptr("pre"), ptr("cls"),
-                                             ptr("hist")))
+        _lib.check(lib.mdc_predict_q612_raw_host(self._h.ptr, xa.ctypes.data, fmt, n, ptr("out"), ptr("pre"), ptr("cls"),
+                                                 ptr("hist")))
         if "hist" in out:
             out["hist"] = out["hist"].astype(np.int64)
         return out
 
     def predict(self, x, output: str = "out"):
         """x int32 [N,256] (0-127 I, 128-255 Q; values are wrapped to 18 bits like a sized
-        Verilog literal).  ``output``: "out" (``out_data``, ReLU'd Q.12 int32 [N,C]),
+        Verilog literal), int16 [N,256] (the same address map, Q6.12) or uint8 [N,128,2] (raw RTL-SDR bytes
+        I0 Q0 I1 Q1 ..., sample = (2u - 255) * 16 as ``sdr.ingest_u8`` writes it).  ``output``: "out" (``out_data``, ReLU'd Q.12 int32 [N,C]),
         "pre" (``pre_out_data``), "argmax"."""
         key = {"out": "out", "pre": "pre", "argmax": "cls"}.get(output)
         if key is None:
@@ -103,13 +121,13 @@ class FixedPointCNN2:
         key = {"out": "out", "pre": "pre", "argmax": "cls"}.get(output)
         if key is None:
             raise ValueError("output must be 'out', 'pre' or 'argmax'")
-        xa = np.ascontiguousarray(x, dtype=np.int32).reshape(-1, 256)
+        xa, fmt = _host_frames(x)
         n = xa.shape[0]
         out = pinned_empty((n,), np.int32) if key == "cls" else pinned_empty((n, self.classes), np.int32)
         ptr = lambda k: out.ctypes.data if k == key else None  # noqa: E731
         ticket = C.c_int64(0)
-        _lib.check(self._h._lib.mdc_predict_q612_host_async(self._h.ptr, xa.ctypes.data, n, ptr("out"), ptr("pre"),
-                                                            ptr("cls"), None, C.byref(ticket)))
+        _lib.check(self._h._lib.mdc_predict_q612_raw_host_async(self._h.ptr, xa.ctypes.data, fmt, n, ptr("out"), ptr("pre"),
+                                                                ptr("cls"), None, C.byref(ticket)))
         return PendingPrediction(self, ticket.value, out, xa)
 
     def class_histogram(self, x):

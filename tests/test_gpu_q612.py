@@ -160,3 +160,43 @@ def test_small_signal_path_is_exact_up_to_its_bound(qsets, k):
         x[:500] = np.where(g.random((500, 256)) < 0.5, -bound, bound)      # all samples at the extreme
         x[500:1000, ::7] = bound
         assert np.array_equal(m.predict(x, output="pre"), sv.forward_pre(x, ct, db, dt)), (k, bound)
+
+
+@pytest.mark.parametrize("geom", ["A", "E", "generic"])
+def test_raw_u8_and_int16_frames(golden, qsets, h5w, geom):
+    """int16 [N,256] (the test_table address map) and raw uint8 I/Q bytes are converted in the frame load: int16 equals
+    the int32 call on the same values, uint8 equals the oracle on (2u - 255) * 16 (what sdr.ingest_u8 writes) - every
+    kernel family (F=3, F=10, generic), host, device and streaming paths."""
+    import torch
+    from modulationdetectioncnn_b200 import export
+    from modulationdetectioncnn_b200.qmodel import FixedPointCNN2
+    from modulationdetectioncnn_b200.svtext import QWeights
+    from oracle import sdr as osdr, sv_datapath as sv
+    if geom == "A":
+        qw = QWeights(*[a.copy() for a in qsets["A"]])
+    elif geom == "E":
+        qw = export.qweights_from_dense_dump(h5w["E_f10"], golden["qweights"]["E_dense_flat"])
+    else:
+        g = philox(5)
+        qw = QWeights(g.integers(-9000, 9000, 3 * 4).astype(np.int32), g.integers(-3000, 3000, 2).astype(np.int32),
+                      g.integers(-6000, 6000, (4, 129 * 4)).astype(np.int32))
+    m = FixedPointCNN2(qw.filters, qw.classes)
+    m.set_tables(qw)
+    n = 16384 + 37
+    q = philox(21).integers(-3000, 3000, (n, 256)).astype(np.int16)
+    q[0, :4] = (-32768, 32767, -1, 0)                     # beyond the small-signal bound: the 36-bit slices
+    want = sv.forward_pre(q.astype(np.int32), qw.conv_tab, qw.dense_bias, qw.dense_tabs)
+    assert np.array_equal(m.predict(q, output="pre"), want)
+    assert np.array_equal(m.predict(torch.from_numpy(q).cuda(), output="pre").cpu().numpy(), want)
+    assert np.array_equal(m.predict_async(q, output="pre").result(), want)
+    raw = philox(22).integers(0, 256, (n, 128, 2), dtype=np.uint8)
+    _, q612, _ = osdr.ingest_u8(raw.reshape(-1))
+    wantu = sv.forward_pre(q612, qw.conv_tab, qw.dense_bias, qw.dense_tabs)
+    assert np.array_equal(m.predict(raw, output="pre"), wantu)
+    assert np.array_equal(m.predict(torch.from_numpy(raw).cuda(), output="pre").cpu().numpy(), wantu)
+    assert np.array_equal(m.predict(raw, output="argmax"), np.maximum(wantu, 0).argmax(-1))
+    for k in (1, 31, 33):
+        assert np.array_equal(m.predict(raw[:k], output="pre"), wantu[:k]), k
+    assert m.class_histogram(raw).tolist() == np.bincount(np.maximum(wantu, 0).argmax(-1), minlength=qw.classes).tolist()
+    from modulationdetectioncnn_b200 import _lib
+    assert m._h._lib.mdc_predict_q612_raw_host(m._h.ptr, raw.ctypes.data, _lib.IN_F32, 1, None, None, None, None) == -1

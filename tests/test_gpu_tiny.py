@@ -116,3 +116,70 @@ def test_large_batch_wraps_the_frame_ring(h5w, tag):
     assert m.class_histogram(x).cpu().numpy().tolist() == np.bincount(cls, minlength=3).tolist()
     for k in (1, 2, 3, 4, 5, 7, 57):
         assert np.array_equal(m.predict(x[:k], output="dense").cpu().numpy(), z[:k]), k
+
+
+@pytest.mark.parametrize("tag", ["A_3conv", "E_f10"])
+def test_back_to_back_launches_and_graph_replay(h5w, tag):
+    """The kernel is launched with programmatic stream serialisation (the next launch's prologue runs under this
+    launch's tail).  Dependent launches chained on one stream - each reading what another kernel has just written, all
+    writing the same output - must see ordered data, and the launch must stay capturable in a CUDA graph."""
+    import torch
+    from modulationdetectioncnn_b200 import _lib
+    from oracle import cnn2_float as cf
+    w = h5w[tag]
+    m = _model(w)
+    lib, h = m._h._lib, m._h
+    n = 20000
+    base = philox(7).normal(0, 2 ** -7, (n, 2, 128)).astype(np.float32)
+    want = cf.tiny_cnn2_forward(base, *w, output="dense")
+    x = torch.empty((n, 2, 128), device="cuda")
+    src = torch.from_numpy(base).cuda()
+    out = torch.empty((n, 3), device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    for rep in range(20):
+        x.copy_(src * float(rep + 1))                     # a producer kernel right in front of the dependent launch
+        _lib.check(lib.mdc_predict_f32(h.ptr, x.data_ptr(), n, None, out.data_ptr(), None, None, st))
+        x.zero_()                                         # and a writer right behind it
+    torch.cuda.synchronize()
+    want20 = cf.tiny_cnn2_forward(base * np.float32(20), *w, output="dense")
+    np.testing.assert_allclose(out.cpu().numpy(), want20, rtol=RTOL, atol=1e-5 * np.abs(want20).max(axis=1, keepdims=True).max())
+    x.copy_(src)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        with torch.cuda.graph(g, stream=s):
+            for _ in range(3):
+                _lib.check(lib.mdc_predict_f32(h.ptr, x.data_ptr(), n, None, out.data_ptr(), None, None, s.cuda_stream))
+    out.zero_()
+    g.replay()
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(out.cpu().numpy(), want, rtol=RTOL, atol=1e-6)
+
+
+@pytest.mark.parametrize("tag", ["A_3conv", "E_f10"])
+def test_raw_u8_and_int16_frames_equal_ingest_then_predict(h5w, tag):
+    """uint8 interleaved I/Q (RTL-SDR bytes) and int16 Q6.12 frames are converted when a lane picks its samples out of
+    the ring: bit-identical to sdr.ingest_u8 -> predict(f32) / to predict(q / 4096) on the host, device and streaming
+    paths, incl. ragged sizes (the ring's last pass) and the sample left of a lane's four (lane 0: zero padding)."""
+    import torch
+    from modulationdetectioncnn_b200 import sdr
+    w = h5w[tag]
+    m = _model(w)
+    n = 16384 + 4099
+    raw = philox(11).integers(0, 256, (n, 128, 2), dtype=np.uint8)
+    f32 = sdr.ingest_u8(torch.from_numpy(raw.reshape(-1)).cuda(), ("f32",))["f32"]
+    want = m.predict(f32, output="dense").cpu().numpy()
+    assert np.abs(want).max() > 0
+    assert np.array_equal(m.predict(raw, output="dense"), want)                                  # host u8
+    assert np.array_equal(m.predict(torch.from_numpy(raw).cuda(), output="dense").cpu().numpy(), want)
+    assert np.array_equal(m.predict_async(raw, output="dense").result(), want)
+    for k in (1, 2, 3, 5, 4099):
+        assert np.array_equal(m.predict(raw[:k], output="dense"), want[:k]), k
+    q = philox(12).integers(-2000, 2000, (n, 2, 128)).astype(np.int16)
+    q[0, :, 0] = (-32768, 32767)
+    wantq = m.predict((q.astype(np.float32) / np.float32(4096)), output="dense")
+    assert np.array_equal(m.predict(q, output="dense"), wantq)
+    assert np.array_equal(m.predict(torch.from_numpy(q).cuda(), output="dense").cpu().numpy(), wantq)
+    assert np.array_equal(m.predict_classes(raw), want.argmax(-1))
+    assert m.class_histogram(raw).tolist() == np.bincount(want.argmax(-1), minlength=3).tolist()

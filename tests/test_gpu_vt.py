@@ -417,14 +417,26 @@ def test_raw_u8_and_int16_frames_equal_ingest_then_predict(vt, mode):
     assert np.array_equal(m.predict_classes(raw), want.argmax(-1))
 
 
-def test_raw_formats_rejected_where_no_kernel_reads_them(h5w):
+def test_raw_formats_rejected_where_no_kernel_reads_them(h5w, vt):
+    """Raw frames are read by the tensor-core VT kernels and the specialised TinyCNN2 kernels; the generic TinyCNN2
+    kernel, the fp32 CUDA-core VT mode and wrong format ids refuse them before anything is launched."""
     from modulationdetectioncnn_b200 import _lib
     from modulationdetectioncnn_b200.model import tiny_cnn2, vt_cnn2
-    m = tiny_cnn2(3, 3)
-    m.set_weights(h5w["A_3conv"])
+    m = tiny_cnn2(4, 2)                                           # no specialisation for this shape
+    g = philox(3)
+    m.set_weights([g.normal(0, 1, (1, 2, 1, 4)).astype(np.float32), np.zeros(4, np.float32),
+                   g.normal(0, 1, (2 * 129 * 4, 2)).astype(np.float32), np.zeros(2, np.float32)])
     with pytest.raises(_lib.MdcError) as e:
         m.predict(np.zeros((4, 128, 2), np.uint8))
     assert e.value.code == -4
+    w, _, _ = vt
+    v = vt_cnn2(11, mode="fp32")
+    v.set_weights(_wlist(w))
+    with pytest.raises(_lib.MdcError) as e:
+        v.predict(np.zeros((4, 256), np.int16))
+    assert e.value.code == -4
+    lib, h = v._h._lib, v._h
+    assert lib.mdc_predict_raw_host(h.ptr, np.zeros(1024, np.uint8).ctypes.data, 3, 1, None, None, None, None) == -1
 
 
 def test_pageable_and_pinned_host_buffers_agree(vt):
