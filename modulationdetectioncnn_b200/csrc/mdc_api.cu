@@ -750,9 +750,7 @@ static int predict_f32_host_impl(mdc_handle_t h, const void* x_host, int in_fmt,
   }
   if (vt_tensor_mode(h))
     return run_vt_host_pipeline(h, x_host, in_fmt, n, probs_host, dense_host, cls_host, hist_host, ticket);
-  // 16 MiB of frames per chunk whatever the format (a narrow format would otherwise mean 4 MiB copies and four
-  // times the launches per byte)
-  const int64_t chunk = (int64_t)16384 * (1024 / (int64_t)frame_bytes(in_fmt));
+  static const int64_t chunk = getenv("MDC_HOST_CHUNK") ? atoll(getenv("MDC_HOST_CHUNK")) : 16384;   // frames per chunk
   return run_host_pipeline<float, float>(
       h, x_host, frame_bytes(in_fmt), n, probs_host, dense_host, cls_host, hist_host, chunk, ticket,
       [h, in_fmt](const void* x, int64_t m, float* p, float* d, int32_t* c, unsigned long long* hs, cudaStream_t s) {
@@ -771,7 +769,7 @@ static int predict_q612_host_impl(mdc_handle_t h, const void* x_host, int in_fmt
     if (hist_host) memset(hist_host, 0, h->C * sizeof(unsigned long long));
     return MDC_OK;
   }
-  const int64_t chunk = (int64_t)16384 * (1024 / (int64_t)frame_bytes(in_fmt));   // 16 MiB of frames per chunk
+  static const int64_t chunk = getenv("MDC_HOST_CHUNK") ? atoll(getenv("MDC_HOST_CHUNK")) : 16384;   // frames per chunk
   return run_host_pipeline<int32_t, int32_t>(
       h, x_host, frame_bytes(in_fmt), n, out_host, pre_host, cls_host, hist_host, chunk, ticket,
       [h, in_fmt](const void* x, int64_t m, int32_t* o, int32_t* p, int32_t* c, unsigned long long* hs, cudaStream_t s) {
