@@ -530,11 +530,8 @@ def other_paths(torch, dev, peaks, _lib):
     pf = torch.empty((n, 3), dtype=torch.float32, device=dev)
     xf_h = torch.from_numpy(synth.iq_frames(nh)).pin_memory().numpy()
     pf_h = np.empty((nh, 3), dtype=np.float32)
-    # issue slots of the arithmetic alone, per frame and warp: an FFMA2 holds the issue port for two cycles
-    # (tools/pipe_rate), so F FFMA2-pairs cost 2 x (2F conv + 3F dense) x 4 slots plus 8F FMNMX for the ReLU
-    tiny_note = ("fp32 FMA and issue slots bind before HBM: an FFMA2 occupies its scheduler's issue port for two cycles "
-                 "(tools/pipe_rate), so the arithmetic alone needs 48 F slots per frame and warp (40 F of FFMA2, 8 F of "
-                 "FMNMX for the ReLU)")
+    tiny_note = ("fp32 FMA pipe and dependent-chain latency bind before HBM: 20 F FFMA2 per frame and warp at two FMA-pipe "
+                 "cycles each, four warps per scheduler (128 registers); ncu: FMA pipe 63 % of cycles, issue slots 60 % (F=10)")
     for tag, label, flop in (("A_3conv", "tiny_f32 F=3 (C3, 3conv checkpoint)", 7740), ("E_f10", "tiny_f32 F=10 (C2a, convmodrecnets_CNN2_0.5)", 25800)):
         w = [hw[f"{tag}_{k}"] for k in ("conv_k", "conv_b", "dense_k", "dense_b")]
         tm = tiny_cnn2(w[0].shape[-1], 3, dev.index)
@@ -546,7 +543,7 @@ def other_paths(torch, dev, peaks, _lib):
             1036, n, UNIT, peaks, torch, h2d=nh * 1024, d2h=nh * 12,
             extra={"dtype": "f32", "flop_per_frame": flop,
                    "fp32_fma_ceiling_frames_per_s": 148 * 128 * 2 * 1.965e9 / flop,
-                   "issue_ceiling_frames_per_s": 148 * 4 * 1.965e9 / (48 * w[0].shape[-1]), "note": tiny_note},
+                   "note": tiny_note},
             host_units=nh,
             host_formats={"u8": (lambda i: _lib.check(tm._h._lib.mdc_predict_raw_host(tm._h.ptr, xu8_h.ctypes.data, _lib.IN_U8IQ, nh, pf_h.ctypes.data, None, None, None)),
                                  nh * 256, "mdc_predict_raw_host(MDC_IN_U8IQ): raw RTL-SDR bytes, (u - 127.5) / 128")}))
@@ -558,7 +555,7 @@ def other_paths(torch, dev, peaks, _lib):
         lambda i: _lib.check(tm._h._lib.mdc_predict_f32(tm._h.ptr, xf[(i % 32) * nb:].data_ptr(), nb, pf.data_ptr(), None, None, None, stream)),
         None, 1036, nb, UNIT, peaks, torch, steps=32, warmup=4,
         extra={"dtype": "f32", "flop_per_frame": 25800, "fp32_fma_ceiling_frames_per_s": 148 * 128 * 2 * 1.965e9 / 25800,
-               "issue_ceiling_frames_per_s": 148 * 4 * 1.965e9 / 480, "note": tiny_note}))
+               "note": tiny_note}))
     del xf, pf
 
     # 8f-4: raw RTL-SDR ingest, 2^28 samples (512 MiB of u8 in, 2 GiB f32 + 2 GiB Q6.12 frames out)

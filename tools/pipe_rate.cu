@@ -38,6 +38,11 @@ __global__ void k(unsigned long long* out, long long* cyc, float seed) {
       if (OP == 11) asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(a[i]) : "l"(b));
       if (OP == 12) asm volatile("mul.rn.f32x2 %0, %0, %1;" : "+l"(a[i]) : "l"(b));
       if (OP == 13) asm volatile("fma.rm.f32 %0, %0, %1, %1;" : "+f"(f[i]) : "f"(fb));
+      if (OP == 15) { asm volatile("fma.rn.f32x2 %0, %0, %1, %1;" : "+l"(a[i]) : "l"(b)); asm volatile("max.f32 %0, %0, %1;" : "+f"(f[i]) : "f"(fb)); }
+      if (OP == 16) { asm volatile("fma.rn.f32x2 %0, %0, %1, %1;" : "+l"(a[i]) : "l"(b)); asm volatile("add.s32 %0, %0, %1;" : "+r"(i32[i]) : "r"(ib)); }
+      if (OP == 17) { asm volatile("mad.lo.s32 %0, %0, %1, %1;" : "+r"(i32[i]) : "r"(ib)); asm volatile("max.f32 %0, %0, %1;" : "+f"(f[i]) : "f"(fb)); }
+      if (OP == 18) { asm volatile("fma.rn.f32 %0, %0, %1, %1;" : "+f"(f[i]) : "f"(fb)); asm volatile("shf.r.wrap.b32 %0, %0, %1, 7;" : "+r"(u[i]) : "r"(ib)); }
+      if (OP == 19) { asm volatile("fma.rn.f32x2 %0, %0, %1, %1;" : "+l"(a[i]) : "l"(b)); asm volatile("max.f32 %0, %0, %1;" : "+f"(f[i]) : "f"(fb)); asm volatile("add.s32 %0, %0, %1;" : "+r"(i32[i]) : "r"(ib)); }
       if (OP == 14) asm volatile("{.reg .f32 lo, hi; mov.b64 {lo, hi}, %0; max.f32 lo, lo, 0f00000000; max.f32 hi, hi, 0f00000000; mov.b64 %0, {lo, hi}; fma.rn.f32x2 %0, %0, %1, %1;}" : "+l"(a[i]) : "l"(b));
     }
   }
@@ -81,5 +86,10 @@ int main() {
   run<12>("FMUL2");
   run<13>("FFMA.RM");
   run<14>("2 FMNMX + FFMA2 (per 3 instr)");
+  run<15>("FFMA2 + FMNMX independent (pair)");
+  run<16>("FFMA2 + IADD independent (pair)");
+  run<17>("IMAD + FMNMX independent (pair)");
+  run<18>("FFMA + SHF independent (pair)");
+  run<19>("FFMA2 + FMNMX + IADD (triple)");
   return 0;
 }
