@@ -17,6 +17,9 @@ __global__ void k(unsigned long long* out, long long* cyc, float seed) {
 #pragma unroll
   for (int i = 0; i < ILP; ++i) { f[i] = seed + i + threadIdx.x; a[i] = (uint64_t)__float_as_uint(f[i]) << 32 | __float_as_uint(f[i] * 0.5f); i32[i] = (int)f[i]; w64[i] = i32[i]; u[i] = i32[i]; }
   const uint64_t b = (uint64_t)__float_as_uint(seed * 0.999f) << 32 | __float_as_uint(seed * 1.001f);
+  uint64_t xx[ILP], yy[ILP];
+#pragma unroll
+  for (int i = 0; i < ILP; ++i) { xx[i] = a[i] ^ 0x0000100000001000ull * (i + 1); yy[i] = a[i] ^ 0x0000020000000200ull * (i + 3); }
   const float fb = seed * 0.999f;
   const int ib = (int)(seed * 77.f) | 1;
   __syncthreads();
@@ -38,6 +41,10 @@ __global__ void k(unsigned long long* out, long long* cyc, float seed) {
       if (OP == 11) asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(a[i]) : "l"(b));
       if (OP == 12) asm volatile("mul.rn.f32x2 %0, %0, %1;" : "+l"(a[i]) : "l"(b));
       if (OP == 13) asm volatile("fma.rm.f32 %0, %0, %1, %1;" : "+f"(f[i]) : "f"(fb));
+      if (OP == 20) asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a[i]) : "l"(xx[i]), "l"(yy[i]));
+      if (OP == 21) asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a[i]) : "l"(xx[0]), "l"(yy[i]));
+      if (OP == 22) asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a[i]) : "l"(xx[i & ~3]), "l"(yy[i]));
+      if (OP == 23) asm volatile("fma.rn.f32 %0, %1, %2, %0;" : "+f"(f[i]) : "f"(__uint_as_float((unsigned)xx[i])), "f"(__uint_as_float((unsigned)yy[i])));
       if (OP == 15) { asm volatile("fma.rn.f32x2 %0, %0, %1, %1;" : "+l"(a[i]) : "l"(b)); asm volatile("max.f32 %0, %0, %1;" : "+f"(f[i]) : "f"(fb)); }
       if (OP == 16) { asm volatile("fma.rn.f32x2 %0, %0, %1, %1;" : "+l"(a[i]) : "l"(b)); asm volatile("add.s32 %0, %0, %1;" : "+r"(i32[i]) : "r"(ib)); }
       if (OP == 17) { asm volatile("mad.lo.s32 %0, %0, %1, %1;" : "+r"(i32[i]) : "r"(ib)); asm volatile("max.f32 %0, %0, %1;" : "+f"(f[i]) : "f"(fb)); }
@@ -49,7 +56,7 @@ __global__ void k(unsigned long long* out, long long* cyc, float seed) {
   const long long t1 = clock64();
   unsigned long long acc = 0;
 #pragma unroll
-  for (int i = 0; i < ILP; ++i) acc += a[i] + __float_as_uint(f[i]) + i32[i] + w64[i] + u[i];
+  for (int i = 0; i < ILP; ++i) acc += a[i] + __float_as_uint(f[i]) + i32[i] + w64[i] + u[i] + xx[i] + yy[i];
   out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
   if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
 }
@@ -86,6 +93,10 @@ int main() {
   run<12>("FMUL2");
   run<13>("FFMA.RM");
   run<14>("2 FMNMX + FFMA2 (per 3 instr)");
+  run<20>("FFMA2 d=a*b+d, 3 distinct register pairs");
+  run<21>("FFMA2 d=X*b+d, X shared by all (reuse)");
+  run<22>("FFMA2 d=X*b+d, X shared by 4 in a row");
+  run<23>("FFMA d=a*b+d, 3 distinct registers");
   run<15>("FFMA2 + FMNMX independent (pair)");
   run<16>("FFMA2 + IADD independent (pair)");
   run<17>("IMAD + FMNMX independent (pair)");
