@@ -530,8 +530,9 @@ def other_paths(torch, dev, peaks, _lib):
     pf = torch.empty((n, 3), dtype=torch.float32, device=dev)
     xf_h = torch.from_numpy(synth.iq_frames(nh)).pin_memory().numpy()
     pf_h = np.empty((nh, 3), dtype=np.float32)
-    tiny_note = ("fp32 FMA pipe and dependent-chain latency bind before HBM: 20 F FFMA2 per frame and warp at two FMA-pipe "
-                 "cycles each, four warps per scheduler (128 registers); ncu: FMA pipe 63 % of cycles, issue slots 60 % (F=10)")
+    tiny_note = ("the register file feeding the FMA pipe binds before HBM: an FFMA2 with three different register-pair "
+                 "operands (activations, the lane's weights, the accumulator) takes 3 cycles, not 2 (tools/pipe_rate): "
+                 "12 F x 3 + 8 F x 2 = 52 F FMA-pipe cycles per frame and scheduler, 520 of the 632 measured for F=10")
     for tag, label, flop in (("A_3conv", "tiny_f32 F=3 (C3, 3conv checkpoint)", 7740), ("E_f10", "tiny_f32 F=10 (C2a, convmodrecnets_CNN2_0.5)", 25800)):
         w = [hw[f"{tag}_{k}"] for k in ("conv_k", "conv_b", "dense_k", "dense_b")]
         tm = tiny_cnn2(w[0].shape[-1], 3, dev.index)
