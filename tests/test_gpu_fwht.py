@@ -54,3 +54,23 @@ def test_full_size_involution():
     assert torch.equal(y[:, 0].to(torch.int64), x.sum(-1))                  # DC bin = sum
     idx = torch.arange(0, s, s // 512, device="cuda")
     assert np.array_equal(y[idx].cpu().numpy(), of.fwht_matrix(x[idx].cpu().numpy()))
+
+
+def test_in_place_allowed_partial_overlap_rejected():
+    """in_dev == out_dev transforms in place (include/mdc.h); any other overlap would let one spectrum's stores land in
+    another's unread input and is refused before anything is launched."""
+    import torch
+    from modulationdetectioncnn_b200 import _lib
+    from oracle import fwht as of
+    lib = _lib.load()
+    x = philox(3).integers(-(1 << 17), 1 << 17, (64, 1024)).astype(np.int32)
+    buf = torch.zeros((65, 1024), dtype=torch.int32, device="cuda")
+    buf[:64] = torch.from_numpy(x).cuda()
+    st = torch.cuda.current_stream().cuda_stream
+    assert lib.mdc_fwht_i32(buf.data_ptr(), buf[1:].data_ptr(), 64, 10, 0, st) == -1          # shifted by one spectrum
+    assert b"overlap" in lib.mdc_last_error()
+    torch.cuda.synchronize()
+    assert np.array_equal(buf[:64].cpu().numpy(), x)                                           # nothing was launched
+    _lib.check(lib.mdc_fwht_i32(buf.data_ptr(), buf.data_ptr(), 64, 10, 0, st))                # in place
+    torch.cuda.synchronize()
+    assert np.array_equal(buf[:64].cpu().numpy(), of.fwht_matrix(x))
