@@ -501,7 +501,7 @@ def other_paths(torch, dev, peaks, _lib):
     hq = torch.zeros(3, dtype=torch.int64, device=dev)
     nh = 1 << 18
     xq_h = torch.from_numpy(synth.q612_frames(nh)).pin_memory().numpy()
-    oq_h = np.empty((nh, 3), dtype=np.int32)
+    oq_h = torch.empty((nh, 3), dtype=torch.int32).pin_memory().numpy()      # pinned in, pinned out (like the headline e2e)
     xq16_h = torch.from_numpy(synth.q612_frames(nh).astype(np.int16)).pin_memory().numpy()
     xu8_h = torch.randint(0, 256, (nh, 128, 2), dtype=torch.uint8).pin_memory().numpy()
     qlib = qm._h._lib
@@ -529,7 +529,7 @@ def other_paths(torch, dev, peaks, _lib):
     xf = torch.randn((n, 2, 128), generator=gen, device=dev).mul_(2.0 ** -7)
     pf = torch.empty((n, 3), dtype=torch.float32, device=dev)
     xf_h = torch.from_numpy(synth.iq_frames(nh)).pin_memory().numpy()
-    pf_h = np.empty((nh, 3), dtype=np.float32)
+    pf_h = torch.empty((nh, 3), dtype=torch.float32).pin_memory().numpy()
     tiny_note = ("the register file feeding the FMA pipe binds before HBM: an FFMA2 with three different register-pair "
                  "operands (activations, the lane's weights, the accumulator) takes 3 cycles, not 2 (tools/pipe_rate): "
                  "12 F x 3 + 8 F x 2 = 52 F FMA-pipe cycles per frame and scheduler, 520 of the 632 measured for F=10")
