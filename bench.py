@@ -516,7 +516,7 @@ def other_paths(torch, dev, peaks, _lib):
         lambda i: _lib.check(qm._h._lib.mdc_predict_q612(qm._h.ptr, xq.data_ptr(), n, oq.data_ptr(), None, None, hq.data_ptr(), stream)),
         lambda i: _lib.check(qm._h._lib.mdc_predict_q612_host(qm._h.ptr, xq_h.ctypes.data, nh, oq_h.ctypes.data, None, None, None)),
         1036, n, UNIT, peaks, torch, h2d=nh * 1024, d2h=nh * 12,
-        extra={"dtype": "int18/36 in int32/int64",
+        extra={"dtype": "int18/36 in int32/int64", "binds": "instruction issue",
                "issue_ceiling_frames_per_s": 148 * 4 * 1.965e9 / 317,
                "note": "instruction-issue-bound, not HBM-bound: 317 warp instructions per frame on the small-signal path "
                        "(204 of them the MACs, shifts and max of the arithmetic itself; ncu: issue slots 83 % busy, L1 90 %, "
@@ -542,7 +542,7 @@ def other_paths(torch, dev, peaks, _lib):
             lambda i: _lib.check(tm._h._lib.mdc_predict_f32(tm._h.ptr, xf.data_ptr(), n, pf.data_ptr(), None, None, None, stream)),
             lambda i: _lib.check(tm._h._lib.mdc_predict_f32_host(tm._h.ptr, xf_h.ctypes.data, nh, pf_h.ctypes.data, None, None, None)),
             1036, n, UNIT, peaks, torch, h2d=nh * 1024, d2h=nh * 12,
-            extra={"dtype": "f32", "flop_per_frame": flop,
+            extra={"dtype": "f32", "flop_per_frame": flop, "binds": "register file / FMA pipe" if flop > 10000 else "hbm, then register file / FMA pipe",
                    "fp32_fma_ceiling_frames_per_s": 148 * 128 * 2 * 1.965e9 / flop,
                    "note": tiny_note},
             host_units=nh,

@@ -138,7 +138,9 @@ MDC_API int mdc_predict_f32(mdc_handle_t h, const float* x_dev, int64_t n, float
 MDC_API int mdc_reserve(mdc_handle_t h, int64_t max_frames);
 
 /* mdc_predict_f32 for frames in one of the MDC_IN_* formats.  MDC_IN_U8IQ / MDC_IN_I16 need a VT-CNN2 handle in a
- * tensor-core mode (BF16, F16X3, TF32X3); x_dev must be 16-byte aligned.                                          */
+ * tensor-core mode (BF16, F16X3, TF32X3) or a TinyCNN2 fp32 handle of a shipped shape (F = 3 or 10, C = 3); other
+ * handles answer MDC_ERR_UNSUPPORTED.  Results are bit-identical to mdc_sdr_ingest_u8 (or s / 4096) followed by
+ * mdc_predict_f32.  x_dev must be 16-byte aligned.                                                                */
 MDC_API int mdc_predict_raw(mdc_handle_t h, const void* x_dev, int in_format, int64_t n, float* probs_dev,
                             float* dense_dev, int32_t* cls_dev, unsigned long long* hist_dev, void* stream);
 
