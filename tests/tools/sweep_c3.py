@@ -1,7 +1,7 @@
 """BASELINE configs[2] / SURVEY C3: checkpoint sweep and precision-mode tolerances on the GPU.
 
 For each shipped checkpoint (the four `2/3/4/5conv` retrains, F=3, and the 10-filter `convmodrecnets_CNN2_0.5`)
-and for the VT-CNN2 stack in its three arithmetic modes, compare the CUDA path with the fp64 oracle on the same
+and for the VT-CNN2 stack in its four arithmetic modes, compare the CUDA path with the fp64 oracle on the same
 synthetic frames: max error of the last Dense output relative to the frame's largest |value|, max |softmax| error,
 argmax agreement.  Test tool: uses oracle/ as the checker.
 
@@ -50,7 +50,7 @@ def main():
             rows.append({"model": f"TinyCNN2 F={w[0].shape[-1]} {name}", "mode": "fp32", "frames": len(xx), "input": label, **r})
     wv = synth.vt_cnn2_weights(11, 1602)
     kw = cf.vt_cnn2_init(11, 1602)
-    for mode, n in (("fp32", 2048), ("tf32x3", 8192), ("bf16", 8192)):
+    for mode, n in (("fp32", 2048), ("f16x3", 8192), ("tf32x3", 8192), ("bf16", 8192)):
         xx = x[:n].copy()
         xx[: n // 8] *= 64
         ref_z = cf.vt_cnn2_forward(xx, **kw, output="logits")
