@@ -440,6 +440,8 @@ def run_ours(args):
                    "parallelism": f"frame-sharded dp{world}, one NCCL all-reduce of int64[11] histogram",
                    "numa_node_of_rank0": numa_node},
         "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk.summary(),
+        # the all-reduced class histogram of the timed steps sums to exactly the frames classified (asserted above)
+        "checks": {"frames_classified": int(frames_all), "class_histogram": [int(v) for v in total_hist.tolist()]},
     }
 
     # ---------------- rank 0, N=1: the other arithmetic modes of the same workload, CPU baseline, HBM-bound paths
