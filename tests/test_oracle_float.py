@@ -77,3 +77,27 @@ def test_crossentropy_matches_definition():
     y = np.array([[1, 0, 0], [0, 1, 0]])
     want = -(np.log(0.7) + np.log(1e-7)) / 2
     assert abs(cf.categorical_crossentropy(p, y) - want) < 1e-12
+
+
+def test_torch_cpu_standin_computes_the_same_nets(h5w):
+    """The CPU baseline / reference arm of bench.py (oracle/cnn2_torch_cpu.py: torch conv2d + matmul, a second,
+    independent statement of both layer stacks) agrees with the numpy restatement - for every shipped checkpoint and for
+    VT-CNN2 with the benchmark's synthetic weights - so the timed stand-in is the function the GPU path is checked
+    against."""
+    from modulationdetectioncnn_b200 import synth
+    from oracle import cnn2_float as cf
+    from oracle.cnn2_torch_cpu import TinyCNN2Cpu, VTCNN2Cpu
+    x = synth.iq_frames(96, seed=5)
+    x[:8] *= 64
+    for tag, w in h5w.items():
+        m = TinyCNN2Cpu(*w)
+        want = cf.tiny_cnn2_forward(x, *w, output="dense")
+        np.testing.assert_allclose(m.predict(x, batch_size=32, output="dense"), want, rtol=1e-5,
+                                   atol=1e-5 * np.abs(want).max(), err_msg=tag)
+        np.testing.assert_allclose(m.predict(x), cf.tiny_cnn2_forward(x, *w), atol=2e-6, err_msg=tag)
+    wv = synth.vt_cnn2_weights(11, 1602)
+    v = VTCNN2Cpu(*wv)
+    ref = cf.vt_cnn2_forward(x, **cf.vt_cnn2_init(11, 1602), output="logits")
+    got = v.predict(x, batch_size=32, output="logits")
+    assert np.abs(got - ref).max() <= 1e-5 * np.abs(ref).max()
+    np.testing.assert_allclose(v.predict(x), cf.vt_cnn2_forward(x, **cf.vt_cnn2_init(11, 1602)), atol=1e-6)
