@@ -34,6 +34,8 @@
 #include <cudaTypedefs.h>
 #include <cuda_fp16.h>
 
+#include <algorithm>
+
 #include "mdc_internal.cuh"
 #include "sm100.cuh"
 
@@ -1054,6 +1056,32 @@ struct DenseF16Smem {
 };
 static_assert(DenseF16Smem::total <= 232448, "f16x3 dense kernel shared memory exceeds 227 KB");
 
+// softmax / argmax / outputs of one frame from its logits (shared by the fused epilogue and vt_head_ordered_kernel so
+// that both produce the same bits); returns the class, -1 for a row past the end
+template <int C>
+__device__ __forceinline__ int head_finish(const float (&z)[C], long long row, long long n, float* __restrict__ probs,
+                                           float* __restrict__ logits_out, int* __restrict__ cls) {
+  float mx = z[0];
+  int best = 0;
+#pragma unroll
+  for (int c = 1; c < C; ++c) if (z[c] > mx) { mx = z[c]; best = c; }
+  if (row >= n) return -1;
+  if (logits_out) {
+#pragma unroll
+    for (int c = 0; c < C; ++c) logits_out[row * C + c] = z[c];
+  }
+  if (probs) {
+    float e[C], sum = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) { e[c] = expf(z[c] - mx); sum += e[c]; }
+    const float inv = 1.0f / sum;
+#pragma unroll
+    for (int c = 0; c < C; ++c) probs[row * C + c] = e[c] * inv;
+  }
+  if (cls) cls[row] = best;
+  return best;
+}
+
 // Partial logits of one frame over this thread's 128 dense1 outputs (column half H): +b3, ReLU, Dense(C) with every
 // W4 element an immediate-offset constant-bank operand (H is a template parameter for exactly that reason).
 template <int C, int H>
@@ -1073,7 +1101,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDenseT32Threads, 1)
 vt_dense_f16x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
                       const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUtensorMap map_bl,
                       const __grid_constant__ HeadW<(C > 0 ? C : 1)> hw, const float* __restrict__ b3g,
-                      float* __restrict__ hbuf, long long n, int num_tiles, float* __restrict__ probs,
+                      float* __restrict__ hbuf, long long n, int num_tiles, int split_pairs, float* __restrict__ probs,
                       float* __restrict__ logits_out, int* __restrict__ cls, unsigned long long* __restrict__ hist) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -1086,10 +1114,26 @@ vt_dense_f16x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_c
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + DenseF16Smem::tmem_slot);
   const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
   const uint32_t rank = cluster_ctarank();      // 0 = leader (issues the pair's MMAs)
-  // the pair walks tiles 2 i and 2 i + 1 in lockstep (a trailing odd tile is all out-of-range rows: zero-filled
-  // loads, no stores)
-  const int tile_first = 2 * (int)cluster_id_x() + (int)rank, tile_step = 2 * (int)cluster_count_x();
-  const int pair_iters = (num_tiles + 1) / 2;       // iterations of pair p: tiles 2 p, 2 p + 1
+  // Work items of this CTA pair.  A pair-tile p is tiles 2 p and 2 p + 1, one per CTA, walked in lockstep (a trailing
+  // odd tile is all out-of-range rows: zero-filled loads, no stores).  The full pair-tiles c, c + G, ... below
+  // `full_pairs` come first; then, when the last round would leave more than half of the pairs idle, ONE OUTPUT HALF
+  // (128 of the 256 dense1 outputs, an N = 128 MMA: half the cycles) of a left-over pair-tile - split_pairs of them,
+  // two CTA pairs each.  Every output is still summed in exactly the order of an unsplit tile, so results do not
+  // depend on where a frame sits in the batch; the halves' h goes to hbuf and vt_head_ordered_kernel finishes them.
+  const int pair_iters = (num_tiles + 1) / 2;
+  const int full_pairs = pair_iters - split_pairs;
+  const int cid = (int)cluster_id_x(), G = (int)cluster_count_x();
+  const int n_full = full_pairs > cid ? (full_pairs - cid + G - 1) / G : 0;
+  const int n_items = n_full + (cid < 2 * split_pairs ? 1 : 0);
+  auto item = [&](int i, int& tile, int& nh) {       // nh: -1 = all 256 outputs, 0 / 1 = outputs [128 nh, 128 nh + 128)
+    if (i < n_full) {
+      tile = 2 * (cid + i * G) + (int)rank;
+      nh = -1;
+    } else {
+      tile = 2 * (full_pairs + (cid >> 1)) + (int)rank;
+      nh = cid & 1;
+    }
+  };
 
   for (int i = tid; i < 256; i += kDenseT32Threads) reinterpret_cast<float*>(smem + DenseF16Smem::b3)[i] = b3g[i];
   if (tid == 0) {
@@ -1116,7 +1160,12 @@ vt_dense_f16x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_c
   if (warp == 0) {
     // ================= TMA: this CTA's frame tile (hi, lo) and its half of the W3 block (hi, lo)
     uint32_t it = 0;
-    for (int tile = tile_first, pit = (int)cluster_id_x(); pit < pair_iters; tile += tile_step, pit += (int)cluster_count_x()) {
+    for (int i = 0; i < n_items; ++i) {
+      int tile, nh;
+      item(i, tile, nh);
+      // this CTA's rows of W3^T: its half of the 256 outputs, or its quarter (64 rows) of an output half - the box
+      // stays 128 rows (rows past 255 are zero-filled), the N = 128 MMA reads the first 64 of them
+      const int brow = nh < 0 ? (int)rank * 128 : nh * 128 + (int)rank * 64;
       for (int kb = 0; kb < kHKBlocks; ++kb, ++it) {
         const uint32_t s = it % kHStages, ph = (it / kHStages) & 1;
         mbar_wait(&empty[s], ph ^ 1);
@@ -1125,8 +1174,8 @@ vt_dense_f16x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_c
           mbar_arrive_expect_tx(&full[s], kHStageBytes);
           tma_load_2d(st, &map_ah, kb * kHK, tile * kTM, &full[s]);
           tma_load_2d(st + kHTile, &map_al, kb * kHK, tile * kTM, &full[s]);
-          tma_load_2d(st + 2 * kHTile, &map_bh, kb * kHK, (int)rank * 128, &full[s]);
-          tma_load_2d(st + 3 * kHTile, &map_bl, kb * kHK, (int)rank * 128, &full[s]);
+          tma_load_2d(st + 2 * kHTile, &map_bh, kb * kHK, brow, &full[s]);
+          tma_load_2d(st + 3 * kHTile, &map_bl, kb * kHK, brow, &full[s]);
         }
         __syncwarp();
       }
@@ -1135,10 +1184,13 @@ vt_dense_f16x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_c
     uint32_t it = 0, run = 0, tcount = 0;
     if (rank == 0) {
       // ================= MMA issuer (whole warp loops, one elected lane issues)
-      const uint32_t idesc = make_idesc_f16(256, 256);
+      const uint32_t idesc_full = make_idesc_f16(256, 256), idesc_half = make_idesc_f16(256, 128);
       const uint32_t base = smem_u32(smem);
       constexpr uint32_t hi = smem_desc_hi(1024, 2);
-      for (int pit = (int)cluster_id_x(); pit < pair_iters; pit += (int)cluster_count_x(), ++tcount) {
+      for (int i = 0; i < n_items; ++i, ++tcount) {
+        int tile, nh;
+        item(i, tile, nh);
+        const uint32_t idesc = nh < 0 ? idesc_full : idesc_half;
         mbar_wait(cross_empty, (tcount & 1) ^ 1);   // the previous tiles' cross sums have been read (both CTAs)
         tc_fence_after_sync();
         for (int r = 0; r < kHRuns; ++r, ++run) {
@@ -1177,7 +1229,7 @@ vt_dense_f16x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_c
       }
     } else {
       // ================= relay (peer CTA): forwards "my stage is full" to the leader's barrier
-      for (int pit = (int)cluster_id_x(); pit < pair_iters; pit += (int)cluster_count_x()) {
+      for (int i = 0; i < n_items; ++i) {
         for (int kb = 0; kb < kHKBlocks; ++kb, ++it) {
           const uint32_t s = it % kHStages, ph = (it / kHStages) & 1;
           mbar_wait(&full[s], ph);
@@ -1189,7 +1241,6 @@ vt_dense_f16x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_c
   } else {
     // ================= epilogue: fold the hi*hi runs into fp32 master sums, add the cross sums, +b3, ReLU -> h
     const int q = warp & 3, half = (warp - 2) >> 2;          // TMEM lane quarter, column half
-    const float* b3s = reinterpret_cast<const float*>(smem + DenseF16Smem::b3) + half * 128;
     uint32_t run = 0, titer = 0;
     unsigned cnt = 0;
     auto release = [&](uint64_t* bar) {           // one arrival per epilogue warp on the LEADER's barrier
@@ -1200,25 +1251,33 @@ vt_dense_f16x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_c
         else mbar_arrive_remote(bar, 0);
       }
     };
-    for (int tile = tile_first, pit = (int)cluster_id_x(); pit < pair_iters; tile += tile_step, pit += (int)cluster_count_x()) {
+    for (int i = 0; i < n_items; ++i) {
+      int tile, nh;
+      item(i, tile, nh);
+      // a thread folds 128 columns of a full tile, 64 of an output half (ng = column groups of 64)
+      const int ng = nh < 0 ? 2 : 1;
+      const int col0 = nh < 0 ? half * 128 : half * 64;                  // first accumulator column of this thread
+      const float* b3s = reinterpret_cast<const float*>(smem + DenseF16Smem::b3) + (nh < 0 ? 0 : nh * 128) + col0;
       float acc[128];
 #pragma unroll
       for (int i = 0; i < 128; ++i) acc[i] = 0.f;
-      const uint32_t tb = tmem + ((uint32_t)(q * 32) << 16) + half * 128;
+      const uint32_t tb = tmem + ((uint32_t)(q * 32) << 16) + col0;
 #pragma unroll 1
       for (int r = 0; r < kHRuns; ++r, ++run) {
         mbar_wait(hh_full, run & 1);
         tc_fence_after_sync();
 #pragma unroll
         for (int g = 0; g < 4; g += 2) {
-          uint32_t v0[32], v1[32];
-          tmem_ld32(tb + g * 32, v0);
-          tmem_ld32(tb + g * 32 + 32, v1);
-          tmem_ld_wait();
+          if (g < 2 * ng) {
+            uint32_t v0[32], v1[32];
+            tmem_ld32(tb + g * 32, v0);
+            tmem_ld32(tb + g * 32 + 32, v1);
+            tmem_ld_wait();
 #pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            acc[g * 32 + e] += __uint_as_float(v0[e]);
-            acc[g * 32 + 32 + e] += __uint_as_float(v1[e]);
+            for (int e = 0; e < 32; ++e) {
+              acc[g * 32 + e] += __uint_as_float(v0[e]);
+              acc[g * 32 + 32 + e] += __uint_as_float(v1[e]);
+            }
           }
         }
         release(hh_empty);
@@ -1226,18 +1285,36 @@ vt_dense_f16x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_c
       // the last run's commit also covers every cross MMA of the tile
 #pragma unroll
       for (int g = 0; g < 4; g += 2) {
-        uint32_t v0[32], v1[32];
-        tmem_ld32(tb + 256 + g * 32, v0);
-        tmem_ld32(tb + 256 + g * 32 + 32, v1);
-        tmem_ld_wait();
+        if (g < 2 * ng) {
+          uint32_t v0[32], v1[32];
+          tmem_ld32(tb + 256 + g * 32, v0);
+          tmem_ld32(tb + 256 + g * 32 + 32, v1);
+          tmem_ld_wait();
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          acc[g * 32 + e] = fmaf(__uint_as_float(v0[e]), 1.f / 2048.f, acc[g * 32 + e]);
-          acc[g * 32 + 32 + e] = fmaf(__uint_as_float(v1[e]), 1.f / 2048.f, acc[g * 32 + 32 + e]);
+          for (int e = 0; e < 32; ++e) {
+            acc[g * 32 + e] = fmaf(__uint_as_float(v0[e]), 1.f / 2048.f, acc[g * 32 + e]);
+            acc[g * 32 + 32 + e] = fmaf(__uint_as_float(v1[e]), 1.f / 2048.f, acc[g * 32 + 32 + e]);
+          }
         }
       }
       release(cross_empty);
       const long long row = (long long)tile * kTM + q * 32 + lane;
+      if (nh >= 0) {
+        // output half: this thread's 64 values of h = relu(. + b3); Dense(C) + softmax follow in vt_head_ordered_kernel
+        if (row < n) {
+          float* dst = hbuf + row * 256 + nh * 128 + col0;
+#pragma unroll
+          for (int e = 0; e < 64; e += 4) {
+            float4 o;
+            o.x = fmaxf(acc[e] + b3s[e], 0.f);
+            o.y = fmaxf(acc[e + 1] + b3s[e + 1], 0.f);
+            o.z = fmaxf(acc[e + 2] + b3s[e + 2], 0.f);
+            o.w = fmaxf(acc[e + 3] + b3s[e + 3], 0.f);
+            *reinterpret_cast<float4*>(dst + e) = o;
+          }
+        }
+        continue;
+      }
       if constexpr (C == 0) {
         if (row < n) {
           float* dst = hbuf + row * 256 + half * 128;
@@ -1269,26 +1346,7 @@ vt_dense_f16x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_c
         if (half == 0) {
 #pragma unroll
           for (int c = 0; c < C; ++c) z[c] += zx[c];
-          float mx = z[0];
-          int best = 0;
-#pragma unroll
-          for (int c = 1; c < C; ++c) if (z[c] > mx) { mx = z[c]; best = c; }
-          if (row >= n) best = -1;
-          if (row < n) {
-            if (logits_out) {
-#pragma unroll
-              for (int c = 0; c < C; ++c) logits_out[row * C + c] = z[c];
-            }
-            if (probs) {
-              float e[C], sum = 0.f;
-#pragma unroll
-              for (int c = 0; c < C; ++c) { e[c] = expf(z[c] - mx); sum += e[c]; }
-              const float inv = 1.0f / sum;
-#pragma unroll
-              for (int c = 0; c < C; ++c) probs[row * C + c] = e[c] * inv;
-            }
-            if (cls) cls[row] = best;
-          }
+          const int best = head_finish<C>(z, row, n, probs, logits_out, cls);
           if (hist) {
 #pragma unroll
             for (int c = 0; c < C; ++c) {
@@ -1309,6 +1367,46 @@ vt_dense_f16x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_c
   __syncthreads();
   cluster_sync_all();
   if (warp == 0) tmem_dealloc_pair<512>(tmem);
+}
+
+// Dense(C) + softmax for the frames whose dense1 outputs came from two output-half items (hbuf holds their h): one
+// thread per frame, the SAME order of operations as the fused epilogue above - the lower 128 outputs accumulate from
+// the bias, the upper 128 from zero, the two partial logits are added last - so these frames get the same bits as
+// frames of unsplit tiles.
+template <int C>
+__global__ void __launch_bounds__(128)
+vt_head_ordered_kernel(const __grid_constant__ HeadW<C> hw, const float* __restrict__ hbuf, long long n,
+                       float* __restrict__ probs, float* __restrict__ logits_out, int* __restrict__ cls,
+                       unsigned long long* __restrict__ hist) {
+  const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const float4* h4 = reinterpret_cast<const float4*>(hbuf + (row < n ? row : n - 1) * 256);
+  float z0[C], z1[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) { z0[c] = hw.b[c]; z1[c] = 0.f; }
+#pragma unroll 4
+  for (int e4 = 0; e4 < 32; ++e4) {
+    const float4 a = h4[e4], b = h4[32 + e4];
+    const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        z0[c] = fmaf(av[j], hw.w[(4 * e4 + j) * C + c], z0[c]);
+        z1[c] = fmaf(bv[j], hw.w[(128 + 4 * e4 + j) * C + c], z1[c]);
+      }
+  }
+  float z[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) z[c] = z0[c] + z1[c];
+  const int best = head_finish<C>(z, row, n, probs, logits_out, cls);
+  if (hist) {
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const unsigned votes = __popc(__ballot_sync(0xffffffffu, best == c));
+      if (lane == c && votes) atomicAdd(hist + c, (unsigned long long)votes);
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1620,18 +1718,38 @@ int launch_vt_dense_head(mdc_handle_s* h, int64_t m, float* probs, float* dense,
     const uint16_t* act = reinterpret_cast<const uint16_t*>(h->ws_act.ptr);
     if (int e = make_kmajor_map(&map_ah, act, (uint64_t)m, kElemF16, kTM)) return e;
     if (int e = make_kmajor_map(&map_al, act + h->vt_act_elems, (uint64_t)m, kElemF16, kTM)) return e;
+    // Last round: with P pair-tiles on G CTA pairs, P mod G pairs would work while the others idle for a whole tile
+    // (65,536 frames: 256 = 3 x 74 + 34).  When at most half of the pairs are busy in that round, each of its
+    // pair-tiles is given to TWO CTA pairs, 128 of the 256 outputs each (the round then costs half a tile); the order
+    // of every sum is unchanged, so the results are bit-identical to unsplit tiles.  Small batches (P <= G / 2) are
+    // split entirely: twice the SMs, half the latency.
+    const int G = pairs_max;
+    int split = pairs < G ? pairs : pairs % G;
+    if (2 * split > G) split = 0;
+    static const bool no_split = getenv("MDC_VT_NO_SPLIT") != nullptr;       // tuning aid
+    if (no_split) split = 0;
+    const unsigned grid_s = 2u * (unsigned)std::max(std::min(pairs - split, G), 2 * split);   // CTAs launched
+    const int64_t m_full = std::min<int64_t>(m, (int64_t)(pairs - split) * 2 * kTM);          // frames of unsplit tiles
     if (h->C == 11) {     // the VT-CNN2 class count: Dense(11) + softmax fused into the epilogue, no head launch
       HeadW<11> hw;
       memcpy(hw.w, h->w[MDC_T_DENSE2_K].data(), sizeof(hw.w));     // Keras (256, C) row-major
       memcpy(hw.b, h->w[MDC_T_DENSE2_B].data(), sizeof(hw.b));
-      vt_dense_f16x3_kernel<11><<<grid_d, kDenseT32Threads, DenseF16Smem::total, stream>>>(
-          map_ah, map_al, wmaps[0], wmaps[1], hw, b3, nullptr, m, tiles, probs, dense, cls, hist);
+      vt_dense_f16x3_kernel<11><<<grid_s, kDenseT32Threads, DenseF16Smem::total, stream>>>(
+          map_ah, map_al, wmaps[0], wmaps[1], hw, b3, hb, m, tiles, split, probs, dense, cls, hist);
       h->launches += 1;
       MDC_CUDA(cudaGetLastError());
+      if (split) {   // the frames of the split tiles: same arithmetic order as the fused epilogue
+        const int64_t rows = m - m_full;
+        vt_head_ordered_kernel<11><<<(unsigned)((rows + 127) / 128), 128, 0, stream>>>(
+            hw, hb + m_full * 256, rows, probs ? probs + m_full * 11 : nullptr, dense ? dense + m_full * 11 : nullptr,
+            cls ? cls + m_full : nullptr, hist);
+        h->launches += 1;
+        MDC_CUDA(cudaGetLastError());
+      }
       return MDC_OK;
     }
-    vt_dense_f16x3_kernel<0><<<grid_d, kDenseT32Threads, DenseF16Smem::total, stream>>>(
-        map_ah, map_al, wmaps[0], wmaps[1], HeadW<1>{}, b3, hb, m, tiles, nullptr, nullptr, nullptr, nullptr);
+    vt_dense_f16x3_kernel<0><<<grid_s, kDenseT32Threads, DenseF16Smem::total, stream>>>(
+        map_ah, map_al, wmaps[0], wmaps[1], HeadW<1>{}, b3, hb, m, tiles, split, nullptr, nullptr, nullptr, nullptr);
   } else {
     const float* act = reinterpret_cast<const float*>(h->ws_act.ptr);
     if (int e = make_kmajor_map(&map_ah, act, (uint64_t)m, kElemF32, kTM)) return e;
