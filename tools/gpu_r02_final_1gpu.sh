@@ -15,7 +15,7 @@ timeout 900 python bench.py --steps 2 --warmup 3 --skip-other > gpurun_out/r02fi
 timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02final_launches.csv python bench.py --steps 2 --warmup 3 --skip-other > gpurun_out/r02final_ncu_launches.log 2>&1
 # full captures: VT f16x3 conv + dense(+head), tiny F=10, tiny F=3
 timeout 300 python tools/prof_vt.py f16x3 65536 1 > gpurun_out/r02final_plain_vt.log 2>&1 && \
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:vt_ -c 2 -f -o gpurun_out/r02_vt_f16x3_v3 python tools/prof_vt.py f16x3 65536 1 > gpurun_out/r02final_ncu_vt.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:vt_ -c 2 -f -o gpurun_out/r02_vt_f16x3_v4 python tools/prof_vt.py f16x3 65536 1 > gpurun_out/r02final_ncu_vt.log 2>&1
 timeout 300 python tools/prof_small.py tiny10 21 1 > gpurun_out/r02final_plain_tiny.log 2>&1 && \
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:tiny -c 1 -f -o gpurun_out/r02_tiny10_v5 python tools/prof_small.py tiny10 21 1 > gpurun_out/r02final_ncu_tiny.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:tiny -c 1 -f -o gpurun_out/r02_tiny3_v5 python tools/prof_small.py tiny3 21 1 >> gpurun_out/r02final_ncu_tiny.log 2>&1
